@@ -1,0 +1,330 @@
+/*
+ * splatt_b200.h -- C ABI of libsplatt_b200.so, the B200-native MTTKRP engine
+ * that drops in behind SPLATT's MTTKRP / CPD-ALS entry points.
+ *
+ * Two groups of symbols:
+ *
+ *  (1) DROP-IN symbols.  Same names, argument meaning, ownership and return
+ *      codes as the reference, so that a SPLATT build can link this library
+ *      in place of src/mttkrp.c (+ src/cpd.c's driver).  Every declaration
+ *      cites the reference declaration it replaces (paths relative to the
+ *      ShadenSmith/splatt tree).  The struct layouts below are written to be
+ *      binary compatible with the reference's default configuration
+ *      (idx = uint64, val = double, SPLATT_MAX_NMODES = 8); tests/test_abi.py
+ *      proves the offsets against the reference headers whenever the reference
+ *      tree is present.
+ *
+ *  (2) ENGINE symbols (prefix splatt_b200_).  The device-resident interface:
+ *      tensors live in HBM as per-mode "fiber streams", factor matrices and
+ *      outputs are device pointers, and a call only enqueues kernels on a CUDA
+ *      stream.  bench.py, the Python host layer and the multi-GPU path use
+ *      these; the drop-in symbols are thin host-buffer wrappers around them.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef SPLATT_B200_H
+#define SPLATT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Scalar types and constants (reference: include/splatt/types_config.h:38-89,
+ * include/splatt/constants.h:14-16, default build widths cmake/types.cmake:3-4)
+ * ---------------------------------------------------------------------- */
+typedef uint64_t splatt_idx_t;
+typedef double   splatt_val_t;
+
+#ifndef SPLATT_MAX_NMODES
+#define SPLATT_MAX_NMODES ((splatt_idx_t) 8)
+#endif
+#define SPLATT_B200_MAX_NMODES 8
+
+/* Return codes (reference: include/splatt/types_config.h:129-137).
+ * NOTE: success is 1, not 0. */
+enum {
+  SPLATT_SUCCESS        = 1,
+  SPLATT_ERROR_BADINPUT = 2,
+  SPLATT_ERROR_NOMEMORY = 3
+};
+
+/* Slots of the `double opts[]` array (reference:
+ * include/splatt/types_config.h:103-123).  The order is ABI. */
+enum {
+  SPLATT_OPTION_NTHREADS   = 0,
+  SPLATT_OPTION_TOLERANCE  = 1,
+  SPLATT_OPTION_REGULARIZE = 2,
+  SPLATT_OPTION_NITER      = 3,
+  SPLATT_OPTION_VERBOSITY  = 4,
+  SPLATT_OPTION_RANDSEED   = 5,
+  SPLATT_OPTION_CSF_ALLOC  = 6,
+  SPLATT_OPTION_TILE       = 7,
+  SPLATT_OPTION_TILELEVEL  = 8,
+  SPLATT_OPTION_PRIVTHRESH = 9,
+  SPLATT_OPTION_DECOMP     = 10,
+  SPLATT_OPTION_COMM       = 11,
+  SPLATT_OPTION_NOPTIONS   = 12
+};
+
+/* reference: include/splatt/types_config.h:143-149 */
+enum { SPLATT_VERBOSITY_NONE = 0, SPLATT_VERBOSITY_LOW, SPLATT_VERBOSITY_HIGH,
+       SPLATT_VERBOSITY_MAX };
+/* reference: include/splatt/types_config.h:155-162 */
+typedef enum { SPLATT_NOTILE = 0, SPLATT_DENSETILE, SPLATT_SYNCTILE,
+               SPLATT_COOPTILE } splatt_tile_type;
+/* reference: include/splatt/types_config.h:168-173 */
+typedef enum { SPLATT_CSF_ONEMODE = 0, SPLATT_CSF_TWOMODE,
+               SPLATT_CSF_ALLMODE } splatt_csf_type;
+
+/* ------------------------------------------------------------------------
+ * Boundary structs.  Layout-compatible with the reference; field names kept
+ * so reference-side code compiles against either header.
+ * ---------------------------------------------------------------------- */
+
+/* One tile's sparsity pattern (reference: include/splatt/structs.h:51-68).
+ * Level l has nfibs[l] nodes; children of node f at level l are
+ * fptr[l][f] .. fptr[l][f+1]-1 at level l+1; fids[l][f] is the node's index
+ * in mode dim_perm[l].  fids[0] may be NULL (root ids are then 0..nfibs[0]-1,
+ * reference: src/csf.c:303-309).  vals has nfibs[nmodes-1] entries. */
+typedef struct
+{
+  splatt_idx_t   nfibs[SPLATT_B200_MAX_NMODES];
+  splatt_idx_t * fptr [SPLATT_B200_MAX_NMODES];
+  splatt_idx_t * fids [SPLATT_B200_MAX_NMODES];
+  splatt_val_t * vals;
+} csf_sparsity;
+
+/* Compressed sparse fiber tensor (reference: include/splatt/structs.h:76-114). */
+typedef struct splatt_csf
+{
+  splatt_idx_t nnz;
+  splatt_idx_t nmodes;
+  splatt_idx_t dims     [SPLATT_B200_MAX_NMODES];
+  splatt_idx_t dim_perm [SPLATT_B200_MAX_NMODES];  /* level -> mode */
+  splatt_idx_t dim_iperm[SPLATT_B200_MAX_NMODES];  /* mode  -> level */
+  splatt_tile_type which_tile;
+  splatt_idx_t ntiles;
+  splatt_idx_t ntiled_modes;
+  splatt_idx_t tile_dims[SPLATT_B200_MAX_NMODES];
+  csf_sparsity * pt;                               /* ntiles entries */
+} splatt_csf;
+
+/* CPD output (reference: include/splatt/structs.h:26-45).  factors[m] and
+ * lambda are malloc()-family memory released by splatt_free_kruskal. */
+typedef struct splatt_kruskal
+{
+  splatt_idx_t   rank;
+  splatt_val_t * factors[SPLATT_B200_MAX_NMODES];
+  splatt_val_t * lambda;
+  splatt_idx_t   nmodes;
+  splatt_idx_t   dims[SPLATT_B200_MAX_NMODES];
+  double         fit;
+} splatt_kruskal;
+
+/* MTTKRP workspace (reference: include/splatt/api_kernels.h:22-67).  Only ever
+ * created by splatt_mttkrp_alloc_ws and handled by pointer, so this library
+ * allocates a larger private object whose first member is this public struct;
+ * the tail carries the device mirror (fiber streams, staging buffers, stream).
+ * The CPU-only fields are filled with the values the reference would compute
+ * where cheap (num_csf, mode_csf_map, num_threads) and NULL/false elsewhere. */
+typedef struct
+{
+  splatt_idx_t   num_csf;
+  splatt_idx_t   mode_csf_map[SPLATT_B200_MAX_NMODES];
+  splatt_idx_t   num_threads;
+  splatt_idx_t * tile_partition[SPLATT_B200_MAX_NMODES];
+  splatt_idx_t * tree_partition[SPLATT_B200_MAX_NMODES];
+  bool           is_privatized[SPLATT_B200_MAX_NMODES];
+  splatt_val_t ** privatize_buffer;
+  double         reduction_time;
+} splatt_mttkrp_ws;
+
+/* Dense matrix used by the internal entry point (reference: src/matrix.h:10-16). */
+typedef struct
+{
+  splatt_idx_t   I;
+  splatt_idx_t   J;
+  splatt_val_t * vals;
+  int            rowmajor;
+} splatt_b200_matrix_t;   /* == reference matrix_t */
+
+/* ------------------------------------------------------------------------
+ * (1) DROP-IN symbols
+ * ---------------------------------------------------------------------- */
+
+/* MTTKRP of a CSF tensor with host factor matrices.
+ * Replaces: include/splatt/api_kernels.h:98-104, src/mttkrp.c:1763-1811.
+ *  mode      output mode;  ncolumns = rank R
+ *  tensors   1, 2 or nmodes CSFs according to options[SPLATT_OPTION_CSF_ALLOC]
+ *  matrices  matrices[m] is row-major dims[m] x ncolumns (host); matrices[mode]
+ *            is never read and may alias matout
+ *  matout    dims[mode] x ncolumns, fully overwritten
+ * Returns SPLATT_SUCCESS (1), or SPLATT_ERROR_* with a "SPLATT:" line on stderr.
+ * Like the reference it builds and destroys a workspace per call. */
+int splatt_mttkrp(
+    splatt_idx_t const mode,
+    splatt_idx_t const ncolumns,
+    splatt_csf const * const tensors,
+    splatt_val_t ** matrices,
+    splatt_val_t * const matout,
+    double const * const options);
+
+/* Replaces: include/splatt/api_kernels.h:107-110, src/mttkrp.c:1814-1912.
+ * Builds the device mirror of `tensors` once (all HBM allocation happens here). */
+splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(
+    splatt_csf const * const tensors,
+    splatt_idx_t const ncolumns,
+    double const * const options);
+
+/* Replaces: include/splatt/api_kernels.h:118-119, src/mttkrp.c:1915-1928. */
+void splatt_mttkrp_free_ws(
+    splatt_mttkrp_ws * const ws);
+
+/* The entry the reference's CPD driver, bench harness and tests call
+ * (reference: src/mttkrp.h:19,35-41 `#define mttkrp_csf splatt_mttkrp_csf`,
+ * src/mttkrp.c:1287-1341; call sites src/cpd.c:327, src/bench.c:191,
+ * tests/mttkrp_test.c:75).  mats[m] are reference matrix_t*, the output is
+ * mats[SPLATT_MAX_NMODES] whose I is reset to dims[mode]; `thds` (the CPU
+ * per-thread scratch, src/thd_info.h:25-30) is accepted and ignored. */
+void splatt_mttkrp_csf(
+    splatt_csf const * const tensors,
+    splatt_b200_matrix_t ** mats,
+    splatt_idx_t const mode,
+    void * const thds,
+    splatt_mttkrp_ws * const ws,
+    double const * const opts);
+
+/* CPD-ALS with the MTTKRP on the GPU.
+ * Replaces: include/splatt/api_factorization.h:41-45, src/cpd.c:22-63 and the
+ * loop of src/cpd.c:271-387 (MTTKRP -> normal equations -> normalise -> Gram,
+ * fit from the last mode's MTTKRP). */
+int splatt_cpd_als(
+    splatt_csf const * const tensors,
+    splatt_idx_t const nfactors,
+    double const * const options,
+    splatt_kruskal * factored);
+
+/* Replaces: include/splatt/api_kruskal.h:34-35, src/cpd.c:66-73. */
+void splatt_free_kruskal(
+    splatt_kruskal * factored);
+
+/* Replaces: include/splatt/api_options.h (splatt_default_opts, src/opts.c:10-47;
+ * splatt_free_opts src/opts.c:50-54).  Same defaults. */
+double * splatt_default_opts(void);
+void     splatt_free_opts(double * opts);
+
+
+/* ------------------------------------------------------------------------
+ * (2) ENGINE symbols -- device-resident interface
+ * ---------------------------------------------------------------------- */
+
+/* Opaque handle: a sparse tensor resident in HBM as fiber streams. */
+typedef struct splatt_b200_tensor splatt_b200_tensor;
+
+/* How MTTKRP modes map to device streams. */
+enum {
+  /* one root-oriented stream per mode (every mode runs the root kernel; uses
+   * nmodes x 16 B/nnz of HBM).  Default. */
+  SPLATT_B200_LAYOUT_ALLROOT = 0,
+  /* mirror exactly the CSFs handed in (ONEMODE/TWOMODE/ALLMODE): modes that
+   * are not a root of some CSF run the internal / leaf kernels (atomics). */
+  SPLATT_B200_LAYOUT_ASGIVEN = 1
+};
+
+/* Build-time knobs; zero-initialise for defaults. */
+typedef struct
+{
+  int32_t layout;        /* SPLATT_B200_LAYOUT_*                           */
+  int32_t device;        /* CUDA device ordinal, -1 = current              */
+  int32_t shard_rank;    /* this process's rank among shard_count          */
+  int32_t shard_count;   /* 0/1 = whole tensor; >1 = keep only this rank's
+                            nnz-balanced share of every stream             */
+  int32_t verbosity;     /* SPLATT_VERBOSITY_*                             */
+  int32_t reserved[11];
+} splatt_b200_build_opts;
+
+/* Mirror reference CSF(s) (host memory) into HBM.  `csf_alloc` says how many
+ * CSFs `tensors` holds (SPLATT_CSF_*; reference: src/csf.c:770-814). */
+int splatt_b200_tensor_from_csf(
+    splatt_csf const * tensors,
+    int csf_alloc,
+    splatt_b200_build_opts const * bopts,
+    splatt_b200_tensor ** out);
+
+/* Build straight from coordinate data.  ind[m] has nnz entries (0-based);
+ * pointers are host or device according to `on_device`. */
+int splatt_b200_tensor_from_coo(
+    int nmodes,
+    uint64_t const * dims,
+    uint64_t nnz,
+    uint32_t const * const * ind,
+    double const * vals,
+    int on_device,
+    int csf_alloc,
+    splatt_b200_build_opts const * bopts,
+    splatt_b200_tensor ** out);
+
+void splatt_b200_tensor_free(splatt_b200_tensor * t);
+
+/* Introspection: *nnz_local is what this shard holds. */
+int splatt_b200_tensor_info(
+    splatt_b200_tensor const * t,
+    int * nmodes, uint64_t * dims, uint64_t * nnz_total, uint64_t * nnz_local,
+    uint64_t * device_bytes);
+
+/* Per-mode facts used for the roofline: kernel kind (0 root, 1 internal,
+ * 2 leaf), level order, node counts per level, algorithmic bytes moved by
+ * one launch at rank R (SURVEY.md section 8d formula at the widths stored). */
+int splatt_b200_mode_info(
+    splatt_b200_tensor const * t, int mode, int ncolumns,
+    int * kind, int * level_perm, uint64_t * nfibs, uint64_t * alg_bytes);
+
+/* Materialise a host splatt_csf array equal to what the reference's
+ * csf_alloc would build from the same nonzeros (reference: src/csf.c:770-814,
+ * :468-502; untiled only).  Arrays are malloc()ed; release with
+ * splatt_b200_csf_free. */
+int splatt_b200_csf_alloc(
+    int nmodes, uint64_t const * dims, uint64_t nnz,
+    uint32_t const * const * ind, double const * vals, int on_device,
+    int csf_alloc, splatt_csf ** out);
+void splatt_b200_csf_free(splatt_csf * csf, int csf_alloc);
+
+/* Host logic, no GPU needed: the level orders csf_alloc would use for each CSF
+ * of an allocation policy (perms: ncsf x SPLATT_B200_MAX_NMODES ints, row c =
+ * level -> mode of CSF c; reference: csf_find_mode_order src/csf.c:694-726) and
+ * the mode -> CSF map of the MTTKRP workspace (reference: src/mttkrp.c:1832-1861).
+ * Returns the number of CSFs, 0 on a bad policy. */
+int splatt_b200_level_orders(
+    uint64_t const * dims, int nmodes, int csf_alloc, int * perms, int * mode_csf_map);
+
+/* Enqueue one MTTKRP on `stream` (a cudaStream_t passed as void*; NULL =
+ * default stream).  d_mats[m] are DEVICE pointers, row-major with leading
+ * dimension ldm (>= ncolumns, even so rows are 16-byte aligned); d_mats[mode]
+ * is ignored.  d_out (dims[mode] x ldm) is zeroed and then accumulated into.
+ * No host synchronisation.  Sharded tensors produce a partial sum that the
+ * caller all-reduces (NCCL). */
+int splatt_b200_mttkrp(
+    splatt_b200_tensor const * t,
+    int mode,
+    int ncolumns,
+    int ldm,
+    double const * const * d_mats,
+    double * d_out,
+    void * stream);
+
+/* Number of kernels the engine has launched in this process (bench.py's
+ * gpu_launches evidence). */
+uint64_t splatt_b200_launch_count(void);
+
+/* Library / build identification, e.g. "splatt_b200 0.1 sm_100a". */
+char const * splatt_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLATT_B200_H */

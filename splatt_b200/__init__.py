@@ -1,0 +1,11 @@
+"""splatt_b200 -- a B200-native MTTKRP engine behind SPLATT's C API.
+
+The product is splatt_b200/libsplatt_b200.so (hand-written sm_100a CUDA, C ABI in
+include/splatt_b200.h).  This package is the thin Python host layer over it.
+"""
+from . import _abi  # noqa: F401
+from .api import (Csf, MttkrpWorkspace, SplattError, Tensor, cpd_als, csf_alloc,  # noqa: F401
+                  default_opts, launch_count, mttkrp)
+
+__all__ = ["Csf", "MttkrpWorkspace", "SplattError", "Tensor", "cpd_als", "csf_alloc",
+           "default_opts", "launch_count", "mttkrp"]

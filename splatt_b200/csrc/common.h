@@ -1,0 +1,126 @@
+// Shared declarations of the splatt_b200 engine (host side + kernel arguments).
+//
+// Data layout in HBM -- the "fiber stream"
+// ----------------------------------------
+// A CSF tensor with level order perm[0..N-1] (root .. leaf; reference:
+// include/splatt/structs.h:76-114) is stored as a linearised tree:
+//
+//   rec[n]     one 16-byte record per nonzero, in CSF (lexicographic) order:
+//                { double v; uint32 k; uint32 aux }
+//                k   = leaf index (mode perm[N-1])
+//                aux = parent index (mode perm[N-2]) in bits 0..28,
+//                      close count c in bits 29..31: how many ancestor levels
+//                      END after this nonzero (c>=1: the level-(N-2) fiber
+//                      ends, c>=2: its level-(N-3) parent ends too, ...,
+//                      c==N-1: the root slice ends).  This replaces the
+//                      reference's fptr[] arrays: the tree is walked by
+//                      counting, never by pointer chasing.
+//   up[l][f]   uint32 index (mode perm[l]) of node f at level l, l = 0..N-3
+//                (the reference's fids[l], always materialised for l = 0).
+//   desc[c][l] for every chunk of SPB200_CHUNK records, the node number at
+//                level l (l = 0..N-3) that contains the chunk's first record,
+//                so any chunk boundary is a legal place to start a traversal.
+//
+// Everything a traversal needs arrives as three perfectly sequential streams
+// (rec, up[*], desc); the only random accesses are the factor-row gathers.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/splatt_b200.h"
+
+#define SPB200_MAXN 8
+#define SPB200_CHUNK 64u             // records per descriptor chunk
+#define SPB200_IDX_BITS 29           // parent index bits in rec.aux
+#define SPB200_IDX_MASK 0x1fffffffu
+
+struct __align__(16) SpRec {
+  double   v;
+  uint32_t k;
+  uint32_t aux;
+};
+static_assert(sizeof(SpRec) == 16, "record must be 16 bytes");
+
+// One sorted stream, device resident (a shard holds a contiguous chunk range).
+struct FiberStream {
+  int      nmodes = 0;
+  int      perm[SPB200_MAXN] = {0};       // level -> mode
+  uint64_t nrec = 0;                       // records held (local)
+  uint64_t nrec_total = 0;                 // records in the whole tensor
+  uint64_t nnodes[SPB200_MAXN] = {0};     // nodes per level (whole tensor)
+  SpRec *    rec = nullptr;
+  uint32_t * up[SPB200_MAXN] = {nullptr}; // levels 0..N-3 (whole arrays)
+  uint32_t * desc = nullptr;               // local chunks x (N-2)
+  uint64_t nchunks = 0;                    // local chunks
+  size_t   bytes = 0;                      // HBM held
+};
+
+enum { SPB200_KIND_ROOT = 0, SPB200_KIND_INTL = 1, SPB200_KIND_LEAF = 2 };
+
+struct ModePlan {
+  int stream = -1;
+  int kind = SPB200_KIND_ROOT;
+  int outdepth = 0;
+};
+
+struct splatt_b200_tensor {
+  int      nmodes = 0;
+  uint64_t dims[SPB200_MAXN] = {0};
+  uint64_t nnz_total = 0;
+  int      device = 0;
+  int      layout = 0;
+  int      shard_rank = 0, shard_count = 1;
+  std::vector<FiberStream> streams;
+  ModePlan plan[SPB200_MAXN];
+};
+
+// Kernel argument block (passed by value).
+struct MttkrpArgs {
+  const SpRec *    rec;
+  const uint32_t * up[SPB200_MAXN - 2];
+  const uint32_t * desc;
+  const double *   mats[SPB200_MAXN];   // by LEVEL: factor of mode perm[l]
+  double *         out;
+  unsigned long long nrec;
+  unsigned int     nchunks;
+  int              ldm;       // leading dimension of every matrix (doubles, even)
+  int              ncols;     // active columns in this launch (even, <= 2*L)
+  int              col0;      // first column of this launch
+  int              outdepth;  // level of the output mode
+};
+
+#define SPB200_CUDA_OK(call)                                                   \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      fprintf(stderr, "SPLATT: CUDA error '%s' at %s:%d (%s)\n",               \
+              cudaGetErrorString(e_), __FILE__, __LINE__, #call);              \
+      return (e_ == cudaErrorMemoryAllocation) ? SPLATT_ERROR_NOMEMORY         \
+                                               : SPLATT_ERROR_BADINPUT;        \
+    }                                                                          \
+  } while (0)
+
+// stream_build.cu -----------------------------------------------------------
+// Build one stream from device COO (ind[m] uint32[nnz], vals) in level order
+// `perm`.  If `presorted`, the input is already lexicographically sorted in
+// that order.  Keeps only this shard's chunk range.
+int spb200_build_stream(int nmodes, const uint64_t * dims, uint64_t nnz,
+                        const uint32_t * const * d_ind, const double * d_vals,
+                        const int * perm, bool presorted,
+                        int shard_rank, int shard_count,
+                        FiberStream * out);
+void spb200_free_stream(FiberStream * s);
+
+// Host CSF arrays from device COO (for splatt_b200_csf_alloc).
+int spb200_build_host_csf(int nmodes, const uint64_t * dims, uint64_t nnz,
+                          const uint32_t * const * d_ind, const double * d_vals,
+                          const int * perm, splatt_csf * csf);
+
+// mttkrp_launch.cu ------------------------------------------------------------
+int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
+                         int ncolumns, int ldm,
+                         const double * const * d_mats_by_mode, double * d_out,
+                         uint64_t out_rows, cudaStream_t stream);
+extern unsigned long long g_spb200_launches;

@@ -1,0 +1,242 @@
+// Drop-in symbols (include/splatt_b200.h, group 1): host-buffer wrappers with the
+// reference's names and semantics around the device engine.
+#include "common.h"
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void spb200_mode_csf_map(int N, int csf_alloc, const int perm0[SPB200_MAXN], int * map);
+
+namespace {
+
+constexpr uint64_t kWsMagic = 0x53504232303057ull;   // "SPB200W"
+
+// Private workspace: the public struct first (callers only hold a pointer to it,
+// reference: src/cpd.c:304, src/mttkrp.c:1796), engine state behind it.
+struct WsPriv {
+  splatt_mttkrp_ws pub;
+  uint64_t magic;
+  splatt_b200_tensor * T;
+  int N;
+  uint64_t dims[SPB200_MAXN];
+  int ncolumns;
+  int ldm;
+  double * d_mats[SPB200_MAXN];
+  double * d_out;
+  uint64_t out_rows_cap;
+  cudaStream_t stream;
+  double last_ms;
+};
+
+int layout_from_env() {
+  const char * e = getenv("SPLATT_B200_LAYOUT");
+  if (e && (!strcmp(e, "asgiven") || !strcmp(e, "ASGIVEN") || !strcmp(e, "1")))
+    return SPLATT_B200_LAYOUT_ASGIVEN;
+  return SPLATT_B200_LAYOUT_ALLROOT;
+}
+
+void free_priv(WsPriv * w) {
+  if (!w) return;
+  for (int m = 0; m < SPB200_MAXN; ++m)
+    if (w->d_mats[m]) cudaFree(w->d_mats[m]);
+  if (w->d_out) cudaFree(w->d_out);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  if (w->T) splatt_b200_tensor_free(w->T);
+  w->magic = 0;
+  free(w);
+}
+
+// Copy a host row-major I x J matrix into a device I x ldm buffer.
+cudaError_t h2d_matrix(double * dst, int ldm, const double * src, uint64_t I, uint64_t J,
+                       cudaStream_t s) {
+  if ((uint64_t)ldm == J) return cudaMemcpyAsync(dst, src, I * J * 8, cudaMemcpyHostToDevice, s);
+  return cudaMemcpy2DAsync(dst, (size_t)ldm * 8, src, J * 8, J * 8, I, cudaMemcpyHostToDevice, s);
+}
+cudaError_t d2h_matrix(double * dst, const double * src, int ldm, uint64_t I, uint64_t J,
+                       cudaStream_t s) {
+  if ((uint64_t)ldm == J) return cudaMemcpyAsync(dst, src, I * J * 8, cudaMemcpyDeviceToHost, s);
+  return cudaMemcpy2DAsync(dst, J * 8, src, (size_t)ldm * 8, J * 8, I, cudaMemcpyDeviceToHost, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
+                                          splatt_idx_t const ncolumns,
+                                          double const * const opts) {
+  if (!tensors || !opts || ncolumns == 0) {
+    fprintf(stderr, "SPLATT: splatt_mttkrp_alloc_ws: bad arguments\n");
+    return nullptr;
+  }
+  const int csf_alloc = (int)opts[SPLATT_OPTION_CSF_ALLOC];
+  if (csf_alloc < SPLATT_CSF_ONEMODE || csf_alloc > SPLATT_CSF_ALLMODE) {
+    // reference: src/mttkrp.c:1856-1858
+    fprintf(stderr, "SPLATT: CSF type '%d' not recognized.\n", csf_alloc);
+    abort();
+  }
+  WsPriv * w = static_cast<WsPriv *>(calloc(1, sizeof(WsPriv)));
+  if (!w) return nullptr;
+  w->magic = kWsMagic;
+  const int N = (int)tensors[0].nmodes;
+  w->N = N;
+  for (int m = 0; m < N; ++m) w->dims[m] = tensors[0].dims[m];
+
+  // public, CPU-facing fields (reference: src/mttkrp.c:1822-1880)
+  w->pub.num_threads = (splatt_idx_t)opts[SPLATT_OPTION_NTHREADS];
+  int perm0[SPB200_MAXN], map[SPB200_MAXN];
+  for (int l = 0; l < N; ++l) perm0[l] = (int)tensors[0].dim_perm[l];
+  spb200_mode_csf_map(N, csf_alloc, perm0, map);
+  for (int m = 0; m < N; ++m) w->pub.mode_csf_map[m] = (splatt_idx_t)map[m];
+  w->pub.num_csf = csf_alloc == SPLATT_CSF_ONEMODE ? 1 : (csf_alloc == SPLATT_CSF_TWOMODE ? 2 : N);
+  w->pub.privatize_buffer = nullptr;
+  w->pub.reduction_time = 0.;
+
+  splatt_b200_build_opts bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.layout = layout_from_env();
+  bo.device = -1;
+  bo.verbosity = (int)opts[SPLATT_OPTION_VERBOSITY];
+  if (splatt_b200_tensor_from_csf(tensors, csf_alloc, &bo, &w->T) != SPLATT_SUCCESS) {
+    free_priv(w);
+    return nullptr;
+  }
+  w->ncolumns = (int)ncolumns;
+  w->ldm = (int)(ncolumns + (ncolumns & 1));
+  uint64_t maxdim = 0;
+  bool ok = true;
+  for (int m = 0; m < N && ok; ++m) {
+    maxdim = w->dims[m] > maxdim ? w->dims[m] : maxdim;
+    ok = cudaMalloc(&w->d_mats[m], w->dims[m] * (size_t)w->ldm * 8) == cudaSuccess &&
+         cudaMemset(w->d_mats[m], 0, w->dims[m] * (size_t)w->ldm * 8) == cudaSuccess;
+  }
+  w->out_rows_cap = maxdim;
+  ok = ok && cudaMalloc(&w->d_out, maxdim * (size_t)w->ldm * 8) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    fprintf(stderr, "SPLATT: out of device memory for MTTKRP workspace (%s)\n",
+            cudaGetErrorString(cudaGetLastError()));
+    free_priv(w);
+    return nullptr;
+  }
+  return &w->pub;
+}
+
+void splatt_mttkrp_free_ws(splatt_mttkrp_ws * const ws) {
+  if (!ws) return;
+  WsPriv * w = reinterpret_cast<WsPriv *>(ws);
+  if (w->magic != kWsMagic) {
+    fprintf(stderr, "SPLATT: splatt_mttkrp_free_ws: workspace was not allocated by "
+                    "libsplatt_b200\n");
+    return;
+  }
+  free_priv(w);
+}
+
+void splatt_mttkrp_csf(splatt_csf const * const tensors, splatt_b200_matrix_t ** mats,
+                       splatt_idx_t const mode, void * const thds, splatt_mttkrp_ws * const ws,
+                       double const * const opts) {
+  (void)thds;
+  WsPriv * w = reinterpret_cast<WsPriv *>(ws);
+  if (!w || w->magic != kWsMagic || !mats || (int)mode >= w->N) {
+    // the reference has no error channel here; fatal like src/mttkrp.c:1857
+    fprintf(stderr, "SPLATT: splatt_mttkrp_csf: workspace not created by libsplatt_b200 "
+                    "or bad mode\n");
+    abort();
+  }
+  const int N = w->N;
+  splatt_b200_matrix_t * M = mats[SPLATT_B200_MAX_NMODES];
+  M->I = tensors[0].dims[mode];                       // reference: src/mttkrp.c:1303-1305
+  const uint64_t J = M->J;
+  if ((int)J != w->ncolumns) {
+    fprintf(stderr, "SPLATT: splatt_mttkrp_csf: workspace built for %d columns, got %llu\n",
+            w->ncolumns, (unsigned long long)J);
+    abort();
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  cudaError_t e = cudaSuccess;
+  for (int m = 0; m < N && e == cudaSuccess; ++m) {
+    if (m == (int)mode) continue;                      // never read (may alias the output)
+    e = h2d_matrix(w->d_mats[m], w->ldm, mats[m]->vals, w->dims[m], J, w->stream);
+  }
+  int rc = SPLATT_SUCCESS;
+  if (e == cudaSuccess)
+    rc = splatt_b200_mttkrp(w->T, (int)mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, w->stream);
+  if (e == cudaSuccess && rc == SPLATT_SUCCESS)
+    e = d2h_matrix(M->vals, w->d_out, w->ldm, w->dims[mode], J, w->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+  if (e != cudaSuccess || rc != SPLATT_SUCCESS) {
+    fprintf(stderr, "SPLATT: GPU MTTKRP failed (%s)\n", cudaGetErrorString(e));
+    abort();
+  }
+  w->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (opts && (int)opts[SPLATT_OPTION_VERBOSITY] == SPLATT_VERBOSITY_MAX) {
+    // counterpart of the per-thread time report, reference: src/mttkrp.c:1333-1339
+    printf("MTTKRP mode %llu: %0.6fs (B200, host buffers)\n", (unsigned long long)mode + 1,
+           w->last_ms * 1e-3);
+  }
+}
+
+int splatt_mttkrp(splatt_idx_t const mode, splatt_idx_t const ncolumns,
+                  splatt_csf const * const tensors, splatt_val_t ** matrices,
+                  splatt_val_t * const matout, double const * const options) {
+  if (!tensors || !matrices || !matout || !options || ncolumns == 0 ||
+      mode >= tensors[0].nmodes) {
+    fprintf(stderr, "SPLATT: splatt_mttkrp: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const int N = (int)tensors[0].nmodes;
+  splatt_mttkrp_ws * ws = splatt_mttkrp_alloc_ws(tensors, ncolumns, options);
+  if (!ws) return SPLATT_ERROR_NOMEMORY;
+  // same wrapping as the reference (src/mttkrp.c:1773-1786)
+  splatt_b200_matrix_t store[SPLATT_B200_MAX_NMODES + 1];
+  splatt_b200_matrix_t * mats[SPLATT_B200_MAX_NMODES + 1] = {nullptr};
+  for (int m = 0; m < N; ++m) {
+    store[m].I = tensors[0].dims[m];
+    store[m].J = ncolumns;
+    store[m].rowmajor = 1;
+    store[m].vals = matrices[m];
+    mats[m] = &store[m];
+  }
+  store[SPLATT_B200_MAX_NMODES].I = tensors[0].dims[mode];
+  store[SPLATT_B200_MAX_NMODES].J = ncolumns;
+  store[SPLATT_B200_MAX_NMODES].rowmajor = 1;
+  store[SPLATT_B200_MAX_NMODES].vals = matout;
+  mats[SPLATT_B200_MAX_NMODES] = &store[SPLATT_B200_MAX_NMODES];
+  splatt_mttkrp_csf(tensors, mats, mode, nullptr, ws, options);
+  splatt_mttkrp_free_ws(ws);
+  return SPLATT_SUCCESS;
+}
+
+double * splatt_default_opts(void) {
+  // reference: src/opts.c:10-47 (SPLATT_VAL_OFF = -DBL_MAX, include/splatt/constants.h)
+  double * opts = static_cast<double *>(malloc(SPLATT_OPTION_NOPTIONS * sizeof(double)));
+  if (!opts) return nullptr;
+  for (int i = 0; i < SPLATT_OPTION_NOPTIONS; ++i) opts[i] = -DBL_MAX;
+  opts[SPLATT_OPTION_TOLERANCE]  = 1e-5;
+  opts[SPLATT_OPTION_REGULARIZE] = 0.;
+  opts[SPLATT_OPTION_NITER]      = 50;
+  opts[SPLATT_OPTION_VERBOSITY]  = SPLATT_VERBOSITY_LOW;
+  opts[SPLATT_OPTION_CSF_ALLOC]  = SPLATT_CSF_TWOMODE;
+  opts[SPLATT_OPTION_TILE]       = SPLATT_NOTILE;
+  opts[SPLATT_OPTION_PRIVTHRESH] = 0.02;
+  opts[SPLATT_OPTION_TILELEVEL]  = 1;
+  opts[SPLATT_OPTION_DECOMP]     = 1;   /* SPLATT_DECOMP_MEDIUM */
+  opts[SPLATT_OPTION_COMM]       = 1;   /* SPLATT_COMM_ALL2ALL  */
+  opts[SPLATT_OPTION_RANDSEED]   = (double)time(nullptr);
+#ifdef _OPENMP
+  opts[SPLATT_OPTION_NTHREADS] = omp_in_parallel() ? 1 : omp_get_max_threads();
+#else
+  opts[SPLATT_OPTION_NTHREADS] = 1;
+#endif
+  return opts;
+}
+
+void splatt_free_opts(double * opts) { free(opts); }
+
+}  // extern "C"

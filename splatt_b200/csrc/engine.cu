@@ -1,0 +1,453 @@
+// Engine entry points (include/splatt_b200.h, group 2): HBM-resident tensors and
+// device-pointer MTTKRP.
+#include "common.h"
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+
+// ---------------------------------------------------------------------------
+// Level orders.  Semantics of csf_find_mode_order (reference: src/csf.c:694-726):
+// SORTED_SMALLFIRST sorts modes by length, ties by mode number
+// (p_order_dims_small :111-136); SORTED_MINUSONE moves one chosen mode to the
+// root and keeps the rest in that order (p_order_dims_minusone :177-195).
+// ---------------------------------------------------------------------------
+void spb200_order_small_first(const uint64_t * dims, int N, int * perm) {
+  for (int m = 0; m < N; ++m) perm[m] = m;
+  std::stable_sort(perm, perm + N, [&](int a, int b) { return dims[a] < dims[b]; });
+}
+void spb200_order_minus_one(const uint64_t * dims, int N, int mode, int * perm) {
+  int tmp[SPB200_MAXN];
+  spb200_order_small_first(dims, N, tmp);
+  perm[0] = mode;
+  int w = 1;
+  for (int i = 0; i < N; ++i)
+    if (tmp[i] != mode) perm[w++] = tmp[i];
+}
+
+// How many CSFs an allocation policy yields and their level orders
+// (reference: csf_alloc src/csf.c:770-814).
+int spb200_csf_orders(const uint64_t * dims, int N, int csf_alloc, int perms[][SPB200_MAXN]) {
+  switch (csf_alloc) {
+    case SPLATT_CSF_ONEMODE:
+      spb200_order_small_first(dims, N, perms[0]);
+      return 1;
+    case SPLATT_CSF_TWOMODE:
+      spb200_order_small_first(dims, N, perms[0]);
+      spb200_order_minus_one(dims, N, perms[0][N - 1], perms[1]);
+      return 2;
+    case SPLATT_CSF_ALLMODE:
+      for (int m = 0; m < N; ++m) spb200_order_minus_one(dims, N, m, perms[m]);
+      return N;
+    default:
+      return 0;
+  }
+}
+
+// Mode -> CSF map of the MTTKRP workspace (reference: src/mttkrp.c:1832-1861).
+void spb200_mode_csf_map(int N, int csf_alloc, const int perm0[SPB200_MAXN], int * map) {
+  for (int m = 0; m < N; ++m) {
+    switch (csf_alloc) {
+      case SPLATT_CSF_ONEMODE: map[m] = 0; break;
+      case SPLATT_CSF_TWOMODE: map[m] = (perm0[N - 1] == m) ? 1 : 0; break;
+      default: map[m] = m; break;
+    }
+  }
+}
+
+namespace {
+
+struct DevCoo {
+  int N = 0;
+  uint64_t nnz = 0;
+  uint32_t * ind[SPB200_MAXN] = {nullptr};
+  double * vals = nullptr;
+  bool owned = false;
+  ~DevCoo() {
+    if (!owned) return;
+    for (int m = 0; m < SPB200_MAXN; ++m)
+      if (ind[m]) cudaFree(ind[m]);
+    if (vals) cudaFree(vals);
+  }
+};
+
+int upload_coo(int N, uint64_t nnz, const uint32_t * const * ind, const double * vals,
+               int on_device, DevCoo * dc) {
+  dc->N = N;
+  dc->nnz = nnz;
+  if (on_device) {
+    for (int m = 0; m < N; ++m) dc->ind[m] = const_cast<uint32_t *>(ind[m]);
+    dc->vals = const_cast<double *>(vals);
+    dc->owned = false;
+    return SPLATT_SUCCESS;
+  }
+  dc->owned = true;
+  for (int m = 0; m < N; ++m) {
+    SPB200_CUDA_OK(cudaMalloc(&dc->ind[m], std::max<uint64_t>(nnz, 1) * 4));
+    SPB200_CUDA_OK(cudaMemcpy(dc->ind[m], ind[m], nnz * 4, cudaMemcpyHostToDevice));
+  }
+  SPB200_CUDA_OK(cudaMalloc(&dc->vals, std::max<uint64_t>(nnz, 1) * 8));
+  SPB200_CUDA_OK(cudaMemcpy(dc->vals, vals, nnz * 8, cudaMemcpyHostToDevice));
+  return SPLATT_SUCCESS;
+}
+
+// Expand one reference CSF (all tiles) to coordinates in storage order.
+// Walks the tree exactly as the reference's kernels do: children of node f at
+// level l are fptr[l][f]..fptr[l][f+1] (include/splatt/structs.h:51-68); the
+// root id is f itself when fids[0] == NULL (src/csf.c:303-309).
+int csf_to_coo(const splatt_csf * ct, std::vector<uint32_t> * ind, std::vector<double> * vals) {
+  const int N = (int)ct->nmodes;
+  const uint64_t nnz = ct->nnz;
+  for (int m = 0; m < N; ++m) ind[m].assign(nnz, 0u);
+  vals->assign(nnz, 0.0);
+  uint64_t off = 0;
+  for (uint64_t t = 0; t < ct->ntiles; ++t) {
+    const csf_sparsity * pt = ct->pt + t;
+    if (pt->vals == nullptr) continue;   // empty tile (src/mttkrp.c:682-685)
+    const uint64_t tn = pt->nfibs[N - 1];
+    if (off + tn > nnz) return SPLATT_ERROR_BADINPUT;
+    memcpy(vals->data() + off, pt->vals, tn * sizeof(double));
+    {
+      uint32_t * dst = ind[ct->dim_perm[N - 1]].data() + off;
+      const splatt_idx_t * src = pt->fids[N - 1];
+#pragma omp parallel for schedule(static)
+      for (int64_t n = 0; n < (int64_t)tn; ++n) dst[n] = (uint32_t)src[n];
+    }
+    // leaf-range start of every node, level by level from the bottom
+    std::vector<uint64_t> ls_child, ls;
+    for (int l = N - 2; l >= 0; --l) {
+      const uint64_t nf = pt->nfibs[l];
+      const splatt_idx_t * fp = pt->fptr[l];
+      ls.resize(nf + 1);
+      if (l == N - 2) {
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = fp[f];
+      } else {
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = ls_child[fp[f]];
+      }
+      uint32_t * dst = ind[ct->dim_perm[l]].data() + off;
+      const splatt_idx_t * ids = pt->fids[l];
+#pragma omp parallel for schedule(dynamic, 256)
+      for (int64_t f = 0; f < (int64_t)nf; ++f) {
+        const uint32_t id = ids ? (uint32_t)ids[f] : (uint32_t)f;
+        for (uint64_t n = ls[f]; n < ls[f + 1]; ++n) dst[n] = id;
+      }
+      ls_child.swap(ls);
+    }
+    off += tn;
+  }
+  return (off == nnz) ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+}
+
+int use_device(int device, int * prev) {
+  SPB200_CUDA_OK(cudaGetDevice(prev));
+  if (device >= 0 && device != *prev) SPB200_CUDA_OK(cudaSetDevice(device));
+  return SPLATT_SUCCESS;
+}
+
+struct PermSpec { int perm[SPB200_MAXN]; bool presorted; };
+
+int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
+                 const std::vector<PermSpec> & stream_perms, const ModePlan * plan,
+                 const splatt_b200_build_opts & bo, splatt_b200_tensor ** out) {
+  splatt_b200_tensor * T = new splatt_b200_tensor();
+  T->nmodes = N;
+  for (int m = 0; m < N; ++m) T->dims[m] = dims[m];
+  T->nnz_total = dc.nnz;
+  T->layout = bo.layout;
+  T->shard_rank = bo.shard_rank;
+  T->shard_count = bo.shard_count > 1 ? bo.shard_count : 1;
+  SPB200_CUDA_OK(cudaGetDevice(&T->device));
+  T->streams.resize(stream_perms.size());
+  for (size_t i = 0; i < stream_perms.size(); ++i) {
+    int rc = spb200_build_stream(N, dims, dc.nnz, dc.ind, dc.vals, stream_perms[i].perm,
+                                 stream_perms[i].presorted, T->shard_rank, T->shard_count,
+                                 &T->streams[i]);
+    if (rc != SPLATT_SUCCESS) { splatt_b200_tensor_free(T); return rc; }
+    if (bo.verbosity >= SPLATT_VERBOSITY_MAX) {
+      const FiberStream & s = T->streams[i];
+      printf("SPLATT-B200: stream %zu order [", i);
+      for (int l = 0; l < N; ++l) printf("%d%s", s.perm[l], l + 1 < N ? " " : "");
+      printf("] nodes [");
+      for (int l = 0; l < N; ++l)
+        printf("%llu%s", (unsigned long long)s.nnodes[l], l + 1 < N ? " " : "");
+      printf("] local records %llu, %.1f MB\n", (unsigned long long)s.nrec, s.bytes / 1e6);
+    }
+  }
+  for (int m = 0; m < N; ++m) T->plan[m] = plan[m];
+  *out = T;
+  return SPLATT_SUCCESS;
+}
+
+bool same_perm(const int * a, const int * b, int N) {
+  for (int l = 0; l < N; ++l)
+    if (a[l] != b[l]) return false;
+  return true;
+}
+
+int kind_of_depth(int depth, int N) {
+  return depth == 0 ? SPB200_KIND_ROOT : (depth == N - 1 ? SPB200_KIND_LEAF : SPB200_KIND_INTL);
+}
+
+}  // namespace
+
+extern "C" {
+
+int splatt_b200_tensor_from_coo(int nmodes, uint64_t const * dims, uint64_t nnz,
+                                uint32_t const * const * ind, double const * vals, int on_device,
+                                int csf_alloc, splatt_b200_build_opts const * bopts,
+                                splatt_b200_tensor ** out) {
+  if (!out || !dims || nmodes < 3 || nmodes > SPB200_MAXN || (nnz && (!ind || !vals))) {
+    fprintf(stderr, "SPLATT: splatt_b200_tensor_from_coo: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  splatt_b200_build_opts bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.device = -1;
+  if (bopts) bo = *bopts;
+  int prev = 0;
+  int rc = use_device(bo.device, &prev);
+  if (rc != SPLATT_SUCCESS) return rc;
+
+  const int N = nmodes;
+  std::vector<PermSpec> sp;
+  ModePlan plan[SPB200_MAXN];
+  if (bo.layout == SPLATT_B200_LAYOUT_ALLROOT) {
+    for (int m = 0; m < N; ++m) {
+      PermSpec p; p.presorted = false;
+      spb200_order_minus_one(dims, N, m, p.perm);
+      sp.push_back(p);
+      plan[m].stream = m; plan[m].kind = SPB200_KIND_ROOT; plan[m].outdepth = 0;
+    }
+  } else {
+    int perms[SPB200_MAXN][SPB200_MAXN];
+    const int nc = spb200_csf_orders(dims, N, csf_alloc, perms);
+    if (nc == 0) {
+      fprintf(stderr, "SPLATT: CSF type '%d' not recognized.\n", csf_alloc);
+      return SPLATT_ERROR_BADINPUT;
+    }
+    for (int c = 0; c < nc; ++c) {
+      PermSpec p; p.presorted = false;
+      memcpy(p.perm, perms[c], sizeof(int) * SPB200_MAXN);
+      sp.push_back(p);
+    }
+    int map[SPB200_MAXN];
+    spb200_mode_csf_map(N, csf_alloc, perms[0], map);
+    for (int m = 0; m < N; ++m) {
+      int depth = 0;
+      for (int l = 0; l < N; ++l)
+        if (perms[map[m]][l] == m) depth = l;
+      plan[m].stream = map[m]; plan[m].outdepth = depth; plan[m].kind = kind_of_depth(depth, N);
+    }
+  }
+  DevCoo dc;
+  rc = upload_coo(N, nnz, ind, vals, on_device, &dc);
+  if (rc == SPLATT_SUCCESS) rc = build_tensor(N, dims, dc, sp, plan, bo, out);
+  if (bo.device >= 0 && bo.device != prev) cudaSetDevice(prev);
+  return rc;
+}
+
+int splatt_b200_tensor_from_csf(splatt_csf const * tensors, int csf_alloc,
+                                splatt_b200_build_opts const * bopts, splatt_b200_tensor ** out) {
+  if (!tensors || !out) return SPLATT_ERROR_BADINPUT;
+  const int N = (int)tensors[0].nmodes;
+  if (N < 3 || N > SPB200_MAXN) {
+    fprintf(stderr, "SPLATT: the B200 engine supports 3..%d modes (got %d)\n", SPB200_MAXN, N);
+    return SPLATT_ERROR_BADINPUT;
+  }
+  int ncsf;
+  switch (csf_alloc) {
+    case SPLATT_CSF_ONEMODE: ncsf = 1; break;
+    case SPLATT_CSF_TWOMODE: ncsf = 2; break;
+    case SPLATT_CSF_ALLMODE: ncsf = N; break;
+    default:
+      fprintf(stderr, "SPLATT: CSF type '%d' not recognized.\n", csf_alloc);
+      return SPLATT_ERROR_BADINPUT;
+  }
+  splatt_b200_build_opts bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.device = -1;
+  if (bopts) bo = *bopts;
+  int prev = 0;
+  int rc = use_device(bo.device, &prev);
+  if (rc != SPLATT_SUCCESS) return rc;
+
+  uint64_t dims[SPB200_MAXN];
+  for (int m = 0; m < N; ++m) dims[m] = tensors[0].dims[m];
+
+  // coordinates in CSF 0's storage order
+  std::vector<uint32_t> ind[SPB200_MAXN];
+  std::vector<double> vals;
+  for (int m = 0; m < N; ++m)
+    if (dims[m] > 0xffffffffull) {
+      fprintf(stderr, "SPLATT: mode %d too long for 32-bit device indices\n", m);
+      return SPLATT_ERROR_BADINPUT;
+    }
+  rc = csf_to_coo(&tensors[0], ind, &vals);
+  if (rc != SPLATT_SUCCESS) {
+    fprintf(stderr, "SPLATT: inconsistent CSF (tile nnz do not add up)\n");
+    return rc;
+  }
+  const bool csf0_sorted = (tensors[0].ntiles == 1);   // untiled storage order is lexicographic
+  int perm0[SPB200_MAXN];
+  for (int l = 0; l < N; ++l) perm0[l] = (int)tensors[0].dim_perm[l];
+
+  std::vector<PermSpec> sp;
+  ModePlan plan[SPB200_MAXN];
+  if (bo.layout == SPLATT_B200_LAYOUT_ALLROOT) {
+    for (int m = 0; m < N; ++m) {
+      PermSpec p; p.presorted = false;
+      // reuse the order of a given CSF rooted at m, else the reference's MINUSONE order
+      bool found = false;
+      for (int c = 0; c < ncsf && !found; ++c)
+        if ((int)tensors[c].dim_perm[0] == m) {
+          for (int l = 0; l < N; ++l) p.perm[l] = (int)tensors[c].dim_perm[l];
+          found = true;
+        }
+      if (!found) spb200_order_minus_one(dims, N, m, p.perm);
+      p.presorted = csf0_sorted && same_perm(p.perm, perm0, N);
+      sp.push_back(p);
+      plan[m].stream = m; plan[m].kind = SPB200_KIND_ROOT; plan[m].outdepth = 0;
+    }
+  } else {
+    for (int c = 0; c < ncsf; ++c) {
+      PermSpec p;
+      for (int l = 0; l < N; ++l) p.perm[l] = (int)tensors[c].dim_perm[l];
+      p.presorted = csf0_sorted && same_perm(p.perm, perm0, N);
+      sp.push_back(p);
+    }
+    int map[SPB200_MAXN];
+    spb200_mode_csf_map(N, csf_alloc, perm0, map);
+    for (int m = 0; m < N; ++m) {
+      const int depth = (int)tensors[map[m]].dim_iperm[m];
+      plan[m].stream = map[m]; plan[m].outdepth = depth; plan[m].kind = kind_of_depth(depth, N);
+    }
+  }
+  const uint32_t * hp[SPB200_MAXN];
+  for (int m = 0; m < N; ++m) hp[m] = ind[m].data();
+  DevCoo dc;
+  rc = upload_coo(N, tensors[0].nnz, hp, vals.data(), 0, &dc);
+  if (rc == SPLATT_SUCCESS) rc = build_tensor(N, dims, dc, sp, plan, bo, out);
+  if (bo.device >= 0 && bo.device != prev) cudaSetDevice(prev);
+  return rc;
+}
+
+void splatt_b200_tensor_free(splatt_b200_tensor * t) {
+  if (!t) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != t->device) cudaSetDevice(t->device);
+  for (auto & s : t->streams) spb200_free_stream(&s);
+  if (prev != t->device) cudaSetDevice(prev);
+  delete t;
+}
+
+int splatt_b200_tensor_info(splatt_b200_tensor const * t, int * nmodes, uint64_t * dims,
+                            uint64_t * nnz_total, uint64_t * nnz_local, uint64_t * device_bytes) {
+  if (!t) return SPLATT_ERROR_BADINPUT;
+  if (nmodes) *nmodes = t->nmodes;
+  if (dims) for (int m = 0; m < t->nmodes; ++m) dims[m] = t->dims[m];
+  if (nnz_total) *nnz_total = t->nnz_total;
+  if (nnz_local) *nnz_local = t->streams.empty() ? 0 : t->streams[0].nrec;
+  if (device_bytes) {
+    uint64_t b = 0;
+    for (auto & s : t->streams) b += s.bytes;
+    *device_bytes = b;
+  }
+  return SPLATT_SUCCESS;
+}
+
+int splatt_b200_mode_info(splatt_b200_tensor const * t, int mode, int ncolumns, int * kind,
+                          int * level_perm, uint64_t * nfibs, uint64_t * alg_bytes) {
+  if (!t || mode < 0 || mode >= t->nmodes) return SPLATT_ERROR_BADINPUT;
+  const ModePlan & p = t->plan[mode];
+  const FiberStream & s = t->streams[p.stream];
+  const int N = t->nmodes;
+  if (kind) *kind = p.kind;
+  if (level_perm) for (int l = 0; l < N; ++l) level_perm[l] = s.perm[l];
+  if (nfibs) for (int l = 0; l < N; ++l) nfibs[l] = s.nnodes[l];
+  if (alg_bytes) {
+    // every array touched once, at the widths stored on device
+    // (values 8 B, indices 4 B; fptr replaced by per-record flags that ride
+    // in the index words, so the fptr term is the 4 B/nnz parent word).
+    const double frac = t->nnz_total ? (double)s.nrec / (double)t->nnz_total : 0.0;
+    uint64_t b = s.nrec * sizeof(SpRec);
+    for (int l = 0; l <= N - 3; ++l) b += (uint64_t)(s.nnodes[l] * frac) * 4;
+    for (int m = 0; m < N; ++m) b += t->dims[m] * (uint64_t)ncolumns * 8;   // N-1 reads + 1 write
+    *alg_bytes = b;
+  }
+  return SPLATT_SUCCESS;
+}
+
+int splatt_b200_mttkrp(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
+                       double const * const * d_mats, double * d_out, void * stream) {
+  if (!t || !d_mats || !d_out || mode < 0 || mode >= t->nmodes) {
+    fprintf(stderr, "SPLATT: splatt_b200_mttkrp: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const ModePlan & p = t->plan[mode];
+  return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
+                              d_out, t->dims[mode], static_cast<cudaStream_t>(stream));
+}
+
+int splatt_b200_csf_alloc(int nmodes, uint64_t const * dims, uint64_t nnz,
+                          uint32_t const * const * ind, double const * vals, int on_device,
+                          int csf_alloc, splatt_csf ** out) {
+  if (!out || !dims || nmodes < 2 || nmodes > SPB200_MAXN) return SPLATT_ERROR_BADINPUT;
+  int perms[SPB200_MAXN][SPB200_MAXN];
+  const int nc = spb200_csf_orders(dims, nmodes, csf_alloc, perms);
+  if (nc == 0) {
+    fprintf(stderr, "SPLATT: CSF type '%d' not recognized.\n", csf_alloc);
+    return SPLATT_ERROR_BADINPUT;
+  }
+  DevCoo dc;
+  int rc = upload_coo(nmodes, nnz, ind, vals, on_device, &dc);
+  if (rc != SPLATT_SUCCESS) return rc;
+  splatt_csf * csf = static_cast<splatt_csf *>(calloc(nc, sizeof(splatt_csf)));
+  if (!csf) return SPLATT_ERROR_NOMEMORY;
+  for (int c = 0; c < nc; ++c) {
+    rc = spb200_build_host_csf(nmodes, dims, nnz, dc.ind, dc.vals, perms[c], &csf[c]);
+    if (rc != SPLATT_SUCCESS) { splatt_b200_csf_free(csf, csf_alloc); return rc; }
+  }
+  *out = csf;
+  return SPLATT_SUCCESS;
+}
+
+void splatt_b200_csf_free(splatt_csf * csf, int csf_alloc) {
+  if (!csf) return;
+  int nc = 1;
+  if (csf_alloc == SPLATT_CSF_TWOMODE) nc = 2;
+  else if (csf_alloc == SPLATT_CSF_ALLMODE) nc = (int)csf[0].nmodes;
+  for (int c = 0; c < nc; ++c) {
+    if (!csf[c].pt) continue;
+    for (uint64_t t = 0; t < csf[c].ntiles; ++t) {
+      free(csf[c].pt[t].vals);
+      for (int l = 0; l < SPB200_MAXN; ++l) {
+        free(csf[c].pt[t].fptr[l]);
+        free(csf[c].pt[t].fids[l]);
+      }
+    }
+    free(csf[c].pt);
+  }
+  free(csf);
+}
+
+int splatt_b200_level_orders(uint64_t const * dims, int nmodes, int csf_alloc, int * perms,
+                             int * mode_csf_map) {
+  if (!dims || nmodes < 1 || nmodes > SPB200_MAXN) return 0;
+  int p[SPB200_MAXN][SPB200_MAXN];
+  const int nc = spb200_csf_orders(dims, nmodes, csf_alloc, p);
+  if (nc == 0) return 0;
+  if (perms)
+    for (int c = 0; c < nc; ++c)
+      for (int l = 0; l < SPB200_MAXN; ++l) perms[c * SPB200_MAXN + l] = l < nmodes ? p[c][l] : 0;
+  if (mode_csf_map) spb200_mode_csf_map(nmodes, csf_alloc, p[0], mode_csf_map);
+  return nc;
+}
+
+uint64_t splatt_b200_launch_count(void) { return g_spb200_launches; }
+
+char const * splatt_b200_version(void) { return "splatt_b200 0.1 (sm_100a fiber-stream MTTKRP)"; }
+
+}  // extern "C"

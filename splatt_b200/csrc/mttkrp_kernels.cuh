@@ -1,0 +1,317 @@
+// sm_100a MTTKRP kernels over fiber streams (see common.h for the layout).
+//
+// Replaces the reference's CPU kernels (src/mttkrp.c):
+//   KIND_ROOT  p_csf_mttkrp_root3_* :390-541, p_csf_mttkrp_root_* :668-799
+//              (with p_propagate_up :324-387)
+//   KIND_INTL  p_csf_mttkrp_intl3_* :544-607/:1032-1093, p_csf_mttkrp_intl_*
+//              :1096-1278
+//   KIND_LEAF  p_csf_mttkrp_leaf3_* :610-665/:802-855, p_csf_mttkrp_leaf_*
+//              :860-1029
+//
+// Execution model
+// ---------------
+//  * A "group" of L lanes owns one record at a time; each lane carries two
+//    adjacent fp64 columns, so a factor row is fetched with one 128-bit load
+//    per lane (L = 16 covers R <= 32, L = 32 covers R <= 64, ...).  A warp
+//    holds 32/L independent groups.
+//  * Every group walks ONE contiguous range of the stream (nnz-balanced:
+//    ranges are equal record counts, not equal slice counts, so skewed slices
+//    cannot unbalance the machine).  The tree is traversed by counting close
+//    flags; partial sums of the levels above the output live in registers and
+//    reach HBM once per finished output node with red.global.add.f64.  A
+//    range boundary is handled by force-closing every level at the range's
+//    last record -- MTTKRP is linear, so a split slice just produces two
+//    partial rows that the reduction adds.  (These are the only atomics of
+//    the root kernel: "atomics only at slice/range boundaries".)
+//  * The record stream is staged through shared memory with 1-D TMA bulk
+//    copies (cp.async.bulk + mbarrier complete_tx), one private 3-stage ring
+//    per warp: no __syncthreads anywhere, the LSU only sees broadcast
+//    LDS.128 (one per record) and the row gathers.
+#pragma once
+#include "common.h"
+
+namespace spb200 {
+
+constexpr int kThreads   = 256;
+constexpr int kWarps     = kThreads / 32;
+constexpr int kStageRecs = 128;   // records per warp per stage (2 KB)
+constexpr int kStages    = 3;
+constexpr int kBatch     = 4;     // records whose gathers are issued together
+
+constexpr size_t kSmemBytes =
+    sizeof(SpRec) * kWarps * kStages * kStageRecs + sizeof(uint64_t) * kWarps * kStages;
+
+__device__ __forceinline__ uint32_t smem_u32(const void * p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t * bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void * dst, const void * src, uint32_t bytes,
+                                             uint64_t * bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ double2 ld_row(const double * __restrict__ base, uint32_t idx, int ldm,
+                                          int col) {
+  return __ldg(reinterpret_cast<const double2 *>(base + static_cast<size_t>(idx) * ldm + col));
+}
+__device__ __forceinline__ void red_row(double * __restrict__ base, uint32_t idx, int ldm, int col,
+                                        double2 x) {
+  double * p = base + static_cast<size_t>(idx) * ldm + col;
+  atomicAdd(p, x.x);      // result unused -> RED.E.ADD.F64
+  atomicAdd(p + 1, x.y);
+}
+__device__ __forceinline__ double2 fma2(double s, double2 a, double2 c) {
+  return make_double2(fma(s, a.x, c.x), fma(s, a.y, c.y));
+}
+__device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) {
+  return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y));
+}
+__device__ __forceinline__ double2 mul2(double2 a, double2 b) {
+  return make_double2(a.x * b.x, a.y * b.y);
+}
+
+template <int N, int L, int KIND>
+__global__ void __launch_bounds__(kThreads, 2) mttkrp_stream_kernel(const MttkrpArgs a) {
+  static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
+  constexpr int G  = 32 / L;            // groups per warp
+  constexpr int SU = kStageRecs / G;    // records per group per stage
+  static_assert(SU % kBatch == 0, "stage must hold whole batches");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SpRec *    srec = reinterpret_cast<SpRec *>(smem_raw);
+  uint64_t * bars =
+      reinterpret_cast<uint64_t *>(smem_raw + sizeof(SpRec) * kWarps * kStages * kStageRecs);
+
+  const int  warp   = threadIdx.x >> 5;
+  const int  lane   = threadIdx.x & 31;
+  const int  grp    = lane / L;
+  const int  gl     = lane % L;
+  const bool act    = (2 * gl) < a.ncols;
+  const bool leader = (gl == 0);
+  const int  col    = a.col0 + 2 * gl;
+  const int  ldm    = a.ldm;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp * kStages + s], G);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // This group's contiguous range of chunks / records.
+  const unsigned long long TG = static_cast<unsigned long long>(gridDim.x) * kWarps * G;
+  const unsigned long long gg =
+      (static_cast<unsigned long long>(blockIdx.x) * kWarps + warp) * G + grp;
+  const unsigned long long cb = gg * a.nchunks / TG;
+  const unsigned long long ce = (gg + 1) * a.nchunks / TG;
+  const unsigned long long rb = cb * SPB200_CHUNK;
+  unsigned long long       re = ce * SPB200_CHUNK;
+  if (re > a.nrec) re = a.nrec;
+  const uint32_t T      = (re > rb) ? static_cast<uint32_t>(re - rb) : 0u;
+  const uint32_t steps  = (T + SU - 1) / SU;
+  const uint32_t wsteps = __reduce_max_sync(0xffffffffu, steps);
+
+  auto issue = [&](uint32_t step) {
+    if (leader) {
+      const uint32_t st  = step % kStages;
+      uint64_t *     bar = &bars[warp * kStages + st];
+      const uint32_t off = step * SU;
+      const uint32_t cnt = (off < T) ? min(static_cast<uint32_t>(SU), T - off) : 0u;
+      if (cnt) {
+        mbar_arrive_expect_tx(bar, cnt * 16u);
+        tma_bulk_g2s(&srec[((warp * kStages + st) * G + grp) * SU], a.rec + rb + off, cnt * 16u,
+                     bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  };
+
+  // Traversal state.
+  const double2 zero2 = make_double2(0.0, 0.0);
+  double2       acc[N - 1];   // partial sums of levels 0..N-2 (levels >= outdepth)
+  double2       pre[N - 1];   // Hadamard prefixes of levels 0..N-2 (levels < outdepth)
+  uint32_t      pos[N - 2];   // current node at levels 0..N-3
+#pragma unroll
+  for (int l = 0; l < N - 1; ++l) { acc[l] = zero2; pre[l] = zero2; }
+#pragma unroll
+  for (int l = 0; l < N - 2; ++l) pos[l] = T ? a.desc[cb * (N - 2) + l] : 0u;
+  uint32_t  pc = N - 1;        // close count of the previous record
+  const int d  = a.outdepth;
+
+#pragma unroll
+  for (int s = 0; s < kStages; ++s)
+    if (s < static_cast<int>(wsteps)) issue(s);
+
+  for (uint32_t step = 0; step < wsteps; ++step) {
+    const uint32_t st = step % kStages;
+    while (!mbar_try_wait(&bars[warp * kStages + st], (step / kStages) & 1u)) {}
+
+    const uint32_t off = step * SU;
+    const uint32_t cnt = (off < T) ? min(static_cast<uint32_t>(SU), T - off) : 0u;
+    SpRec *        buf = &srec[((warp * kStages + st) * G + grp) * SU];
+    // The last record of the range closes every level (range boundary).
+    if (leader && cnt && off + cnt == T)
+      buf[cnt - 1].aux = (buf[cnt - 1].aux & SPB200_IDX_MASK) | (uint32_t(N - 1) << SPB200_IDX_BITS);
+    __syncwarp();
+
+    if constexpr (KIND == SPB200_KIND_ROOT) {
+      for (uint32_t n0 = 0; n0 < cnt; n0 += kBatch) {
+        uint4   q[kBatch];
+        double2 b[kBatch], r[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          q[u] = (n0 + u < cnt) ? *reinterpret_cast<const uint4 *>(&buf[n0 + u])
+                                : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          b[u] = (act && n0 + u < cnt) ? ld_row(a.mats[N - 1], q[u].z, ldm, col) : zero2;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          r[u] = (act && (q[u].w >> SPB200_IDX_BITS))
+                     ? ld_row(a.mats[N - 2], q[u].w & SPB200_IDX_MASK, ldm, col)
+                     : zero2;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const double   v = __hiloint2double(static_cast<int>(q[u].y), static_cast<int>(q[u].x));
+          const uint32_t c = q[u].w >> SPB200_IDX_BITS;
+          acc[N - 2]       = fma2(v, b[u], acc[N - 2]);
+          if (c) {
+            acc[N - 3] = fma2(acc[N - 2], r[u], acc[N - 3]);
+            acc[N - 2] = zero2;
+            if (c >= 2) {
+#pragma unroll
+              for (int l = N - 3; l >= 1; --l) {
+                if (c >= uint32_t(N - 1 - l)) {
+                  const uint32_t idx = __ldg(&a.up[l][pos[l]]);
+                  ++pos[l];
+                  if (act) {
+                    const double2 row = ld_row(a.mats[l], idx, ldm, col);
+                    acc[l - 1]        = fma2(acc[l], row, acc[l - 1]);
+                  }
+                  acc[l] = zero2;
+                }
+              }
+              if (c >= uint32_t(N - 1)) {
+                const uint32_t row = __ldg(&a.up[0][pos[0]]);
+                ++pos[0];
+                if (act) red_row(a.out, row, ldm, col, acc[0]);
+                acc[0] = zero2;
+              }
+            }
+          }
+        }
+      }
+    } else if constexpr (KIND == SPB200_KIND_INTL) {
+#pragma unroll 2
+      for (uint32_t n = 0; n < cnt; ++n) {
+        const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
+        const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+        const uint32_t c   = q.w >> SPB200_IDX_BITS;
+        const uint32_t par = q.w & SPB200_IDX_MASK;
+        const double2  b   = act ? ld_row(a.mats[N - 1], q.z, ldm, col) : zero2;
+        // (re)open prefix levels that changed after the previous record
+        if (pc >= uint32_t(N - d)) {
+#pragma unroll
+          for (int l = 0; l <= N - 3; ++l) {
+            if (l < d && l + int(pc) >= N - 1) {
+              const uint32_t idx = __ldg(&a.up[l][pos[l]]);
+              const double2  row = act ? ld_row(a.mats[l], idx, ldm, col) : zero2;
+              pre[l]             = (l == 0) ? row : mul2(pre[l - 1], row);
+            }
+          }
+        }
+        acc[N - 2] = fma2(v, b, acc[N - 2]);
+        if (c) {
+          // levels below the output level fold upwards
+#pragma unroll
+          for (int l = N - 2; l >= 2; --l) {
+            if (l > d && c >= uint32_t(N - 1 - l)) {
+              uint32_t idx;
+              if (l == N - 2) idx = par;
+              else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
+              if (act) acc[l - 1] = fma2(acc[l], ld_row(a.mats[l], idx, ldm, col), acc[l - 1]);
+              acc[l] = zero2;
+            }
+          }
+          // the output level itself
+#pragma unroll
+          for (int l = 1; l <= N - 2; ++l) {
+            if (l == d && c >= uint32_t(N - 1 - l)) {
+              uint32_t idx;
+              if (l == N - 2) idx = par;
+              else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
+              if (act) red_row(a.out, idx, ldm, col, mul2(pre[l - 1], acc[l]));
+              acc[l] = zero2;
+            }
+          }
+          // prefix levels that ended: advance to their next node
+#pragma unroll
+          for (int l = 0; l <= N - 3; ++l)
+            if (l < d && c >= uint32_t(N - 1 - l)) ++pos[l];
+        }
+        pc = c;
+      }
+    } else {   // KIND_LEAF
+#pragma unroll 2
+      for (uint32_t n = 0; n < cnt; ++n) {
+        const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
+        const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+        const uint32_t c   = q.w >> SPB200_IDX_BITS;
+        const uint32_t par = q.w & SPB200_IDX_MASK;
+        if (pc) {
+#pragma unroll
+          for (int l = 0; l <= N - 2; ++l) {
+            if (l + int(pc) >= N - 1) {
+              uint32_t idx;
+              if (l == N - 2) idx = par;
+              else idx = __ldg(&a.up[l][pos[l]]);
+              const double2 row = act ? ld_row(a.mats[l], idx, ldm, col) : zero2;
+              pre[l]            = (l == 0) ? row : mul2(pre[l - 1], row);
+            }
+          }
+        }
+        if (act) red_row(a.out, q.z, ldm, col, make_double2(v * pre[N - 2].x, v * pre[N - 2].y));
+        if (c) {
+#pragma unroll
+          for (int l = 0; l <= N - 3; ++l)
+            if (c >= uint32_t(N - 1 - l)) ++pos[l];
+        }
+        pc = c;
+      }
+    }
+
+    __syncwarp();
+    if (step + kStages < wsteps) issue(step + kStages);
+  }
+}
+
+}  // namespace spb200

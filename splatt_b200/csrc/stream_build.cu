@@ -1,0 +1,414 @@
+// Device-side construction of fiber streams (and of reference-shaped CSF arrays)
+// from coordinate data.
+//
+// Reference semantics followed (not code): tt_sort orders nonzeros
+// lexicographically by the level permutation (src/sort.c:912-918 via
+// src/csf.c:475); p_mk_outerptr / p_mk_fptr start a new node at level l wherever
+// the index at any level <= l changes (src/csf.c:248-458).  Here the same rule
+// is evaluated per nonzero as "first differing level" dl[n], and everything else
+// (node numbering, fids, fptr, close counts) follows from prefix sums over
+// dl[n] <= l.  Sorting and scans use CUB (one-time set-up, not the hot path).
+#include "common.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+
+namespace {
+
+struct DevBuf {
+  void * p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t b) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = b;
+    return cudaMalloc(&p, b ? b : 16);
+  }
+  template <class T> T * as() { return static_cast<T *>(p); }
+  void * release() { void * r = p; p = nullptr; return r; }
+};
+
+int bits_for(uint64_t dim) {
+  int b = 1;
+  while (b < 64 && (1ull << b) < dim) ++b;
+  return b;
+}
+
+struct KeySpec {
+  const uint32_t * src[SPB200_MAXN];
+  int shift[SPB200_MAXN];
+  int n;
+};
+
+__global__ void k_iota(uint32_t * o, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) o[i] = (uint32_t)i;
+}
+
+__global__ void k_make_keys(KeySpec ks, const uint32_t * __restrict__ order, uint64_t n,
+                            uint64_t * __restrict__ keys) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t o = order[i];
+  uint64_t k = 0;
+  for (int j = 0; j < ks.n; ++j) k |= (uint64_t)ks.src[j][o] << ks.shift[j];
+  keys[i] = k;
+}
+
+__global__ void k_gather_u32(const uint32_t * __restrict__ src, const uint32_t * __restrict__ order,
+                             uint64_t n, uint32_t * __restrict__ dst) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = order ? src[order[i]] : src[i];
+}
+
+struct LevelPtrs { const uint32_t * s[SPB200_MAXN]; };
+
+// dl[n] = first level at which nonzero n differs from n-1 (0 for n == 0,
+// N if all coordinates are equal).
+__global__ void k_first_diff(LevelPtrs lp, int N, uint64_t n, uint8_t * __restrict__ dl) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = 0;
+  if (i > 0) {
+    d = N;
+    for (int l = 0; l < N; ++l)
+      if (lp.s[l][i] != lp.s[l][i - 1]) { d = l; break; }
+  }
+  dl[i] = (uint8_t)d;
+}
+
+__global__ void k_flags(const uint8_t * __restrict__ dl, int level, uint64_t n,
+                        uint32_t * __restrict__ flag) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (dl[i] <= level) ? 1u : 0u;
+}
+
+// nid = inclusive scan of flags.  Node f (= nid-1) starts at position i.
+__global__ void k_scatter_nodes(const uint8_t * __restrict__ dl, int level,
+                                const uint32_t * __restrict__ nid,
+                                const uint32_t * __restrict__ sidx_level, uint64_t n,
+                                uint32_t * __restrict__ ids_out,      // may be null
+                                uint32_t * __restrict__ start_out,    // may be null: position i
+                                const uint32_t * __restrict__ child_nid,  // may be null
+                                uint32_t * __restrict__ child_out) {  // may be null
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n || dl[i] > level) return;
+  const uint32_t f = nid[i] - 1u;
+  if (ids_out) ids_out[f] = sidx_level[i];
+  if (start_out) start_out[f] = (uint32_t)i;
+  if (child_out) child_out[f] = child_nid[i] - 1u;
+}
+
+__global__ void k_desc(const uint32_t * __restrict__ nid, uint64_t n, uint64_t chunk0,
+                       uint64_t nchunks, int level, int stride, uint32_t * __restrict__ desc) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const uint64_t pos = (chunk0 + c) * SPB200_CHUNK;
+  desc[c * stride + level] = nid[pos] - 1u;
+}
+
+__global__ void k_fill_rec(const double * __restrict__ vals, const uint32_t * __restrict__ order,
+                           const uint32_t * __restrict__ leaf, const uint32_t * __restrict__ parent,
+                           const uint8_t * __restrict__ dl, int N, uint64_t n_total, uint64_t first,
+                           uint64_t count, SpRec * __restrict__ rec) {
+  uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const uint64_t i = first + j;
+  uint32_t c;
+  if (i + 1 == n_total) c = (uint32_t)(N - 1);
+  else {
+    const int d = dl[i + 1];
+    c = (d >= N - 1) ? 0u : (uint32_t)(N - 1 - d);
+  }
+  SpRec r;
+  r.v   = vals[order ? order[i] : i];
+  r.k   = leaf[i];
+  r.aux = parent[i] | (c << SPB200_IDX_BITS);
+  rec[j] = r;
+}
+
+__global__ void k_gather_f64(const double * __restrict__ src, const uint32_t * __restrict__ order,
+                             uint64_t n, double * __restrict__ dst) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = order ? src[order[i]] : src[i];
+}
+
+inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
+
+// Sorted view of the COO data in level order.
+struct SortedCoo {
+  int N = 0;
+  uint64_t nnz = 0;
+  DevBuf order;                 // uint32[nnz] (empty if presorted)
+  DevBuf sidx[SPB200_MAXN];     // uint32[nnz] per level
+  DevBuf dl;                    // uint8[nnz]
+  const uint32_t * order_ptr() { return order.p ? order.as<uint32_t>() : nullptr; }
+};
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      fprintf(stderr, "SPLATT: CUDA error '%s' at %s:%d\n", cudaGetErrorString(e_),     \
+              __FILE__, __LINE__);                                                      \
+      return (e_ == cudaErrorMemoryAllocation) ? SPLATT_ERROR_NOMEMORY                  \
+                                               : SPLATT_ERROR_BADINPUT;                 \
+    }                                                                                   \
+  } while (0)
+
+int sort_coo(int N, const uint64_t * dims, uint64_t nnz, const uint32_t * const * d_ind,
+             const int * perm, bool presorted, SortedCoo * sc) {
+  sc->N = N;
+  sc->nnz = nnz;
+  if (nnz >= 0xffffffffull) {
+    fprintf(stderr, "SPLATT: tensors with >= 2^32 nonzeros per device are not supported\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  for (int m = 0; m < N; ++m) {
+    // leaf indices use 32 bits; every other level is a 'parent' in some stream
+    if (dims[m] > (1ull << SPB200_IDX_BITS)) {
+      fprintf(stderr, "SPLATT: mode %d has %llu > 2^%d rows; not supported by the "
+              "device stream format\n", m, (unsigned long long)dims[m], SPB200_IDX_BITS);
+      return SPLATT_ERROR_BADINPUT;
+    }
+  }
+  if (!presorted && nnz > 0) {
+    CK(sc->order.alloc(nnz * 4));
+    DevBuf order_alt, keys, keys_alt, tmp;
+    CK(order_alt.alloc(nnz * 4));
+    CK(keys.alloc(nnz * 8));
+    CK(keys_alt.alloc(nnz * 8));
+    k_iota<<<nblk(nnz), 256>>>(sc->order.as<uint32_t>(), nnz);
+    // LSD passes: pack as many trailing levels as fit into one 64-bit key.
+    int l = N - 1;
+    while (l >= 0) {
+      KeySpec ks; ks.n = 0;
+      int used = 0;
+      while (l >= 0) {
+        const int b = bits_for(dims[perm[l]]);
+        if (used + b > 64) break;
+        ks.src[ks.n] = d_ind[perm[l]];
+        ks.shift[ks.n] = used;
+        ++ks.n;
+        used += b;
+        --l;
+      }
+      k_make_keys<<<nblk(nnz), 256>>>(ks, sc->order.as<uint32_t>(), nnz, keys.as<uint64_t>());
+      cub::DoubleBuffer<uint64_t> kb(keys.as<uint64_t>(), keys_alt.as<uint64_t>());
+      cub::DoubleBuffer<uint32_t> vb(sc->order.as<uint32_t>(), order_alt.as<uint32_t>());
+      size_t tb = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int64_t)nnz, 0, used));
+      if (tb > tmp.bytes) CK(tmp.alloc(tb));
+      CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int64_t)nnz, 0, used));
+      if (vb.Current() != sc->order.as<uint32_t>()) std::swap(sc->order.p, order_alt.p);
+      if (kb.Current() != keys.as<uint64_t>()) std::swap(keys.p, keys_alt.p);
+    }
+    CK(cudaGetLastError());
+  }
+  for (int lv = 0; lv < N; ++lv) {
+    CK(sc->sidx[lv].alloc(nnz * 4));
+    if (nnz)
+      k_gather_u32<<<nblk(nnz), 256>>>(d_ind[perm[lv]], sc->order_ptr(), nnz,
+                                       sc->sidx[lv].as<uint32_t>());
+  }
+  CK(sc->dl.alloc(nnz));
+  if (nnz) {
+    LevelPtrs lp;
+    for (int lv = 0; lv < SPB200_MAXN; ++lv) lp.s[lv] = lv < N ? sc->sidx[lv].as<uint32_t>() : nullptr;
+    k_first_diff<<<nblk(nnz), 256>>>(lp, N, nnz, sc->dl.as<uint8_t>());
+  }
+  CK(cudaGetLastError());
+  return SPLATT_SUCCESS;
+}
+
+// Inclusive scan of (dl <= level) into nid; returns the node count.
+int scan_level(SortedCoo & sc, int level, DevBuf & flag, DevBuf & nid, DevBuf & tmp,
+               uint64_t * nnodes) {
+  const uint64_t nnz = sc.nnz;
+  *nnodes = 0;
+  if (nnz == 0) return SPLATT_SUCCESS;
+  k_flags<<<nblk(nnz), 256>>>(sc.dl.as<uint8_t>(), level, nnz, flag.as<uint32_t>());
+  size_t tb = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, tb, flag.as<uint32_t>(), nid.as<uint32_t>(),
+                                   (int64_t)nnz));
+  if (tb > tmp.bytes) CK(tmp.alloc(tb));
+  CK(cub::DeviceScan::InclusiveSum(tmp.p, tb, flag.as<uint32_t>(), nid.as<uint32_t>(),
+                                   (int64_t)nnz));
+  uint32_t last = 0;
+  CK(cudaMemcpy(&last, nid.as<uint32_t>() + (nnz - 1), 4, cudaMemcpyDeviceToHost));
+  *nnodes = last;
+  return SPLATT_SUCCESS;
+}
+
+}  // namespace
+
+void spb200_free_stream(FiberStream * s) {
+  if (!s) return;
+  if (s->rec) cudaFree(s->rec);
+  for (int l = 0; l < SPB200_MAXN; ++l)
+    if (s->up[l]) cudaFree(s->up[l]);
+  if (s->desc) cudaFree(s->desc);
+  *s = FiberStream();
+}
+
+int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
+                        const uint32_t * const * d_ind, const double * d_vals, const int * perm,
+                        bool presorted, int shard_rank, int shard_count, FiberStream * out) {
+  *out = FiberStream();
+  out->nmodes = N;
+  for (int l = 0; l < N; ++l) out->perm[l] = perm[l];
+  out->nrec_total = nnz;
+
+  SortedCoo sc;
+  int rc = sort_coo(N, dims, nnz, d_ind, perm, presorted, &sc);
+  if (rc != SPLATT_SUCCESS) return rc;
+
+  // shard = contiguous, equal-count range of chunks
+  const uint64_t nchunks_total = (nnz + SPB200_CHUNK - 1) / SPB200_CHUNK;
+  if (shard_count < 1) shard_count = 1;
+  const uint64_t c0 = nchunks_total * (uint64_t)shard_rank / (uint64_t)shard_count;
+  const uint64_t c1 = nchunks_total * (uint64_t)(shard_rank + 1) / (uint64_t)shard_count;
+  const uint64_t r0 = c0 * SPB200_CHUNK;
+  const uint64_t r1 = std::min<uint64_t>(c1 * SPB200_CHUNK, nnz);
+  out->nchunks = c1 - c0;
+  out->nrec = (r1 > r0) ? (r1 - r0) : 0;
+
+  DevBuf flag, nid, tmp, desc;
+  CK(flag.alloc(nnz * 4));
+  CK(nid.alloc(nnz * 4));
+  const int stride = N - 2;
+  CK(desc.alloc(std::max<uint64_t>(out->nchunks, 1) * stride * 4));
+  size_t held = 0;
+  for (int l = 0; l <= N - 2; ++l) {
+    uint64_t nn = 0;
+    rc = scan_level(sc, l, flag, nid, tmp, &nn);
+    if (rc != SPLATT_SUCCESS) { spb200_free_stream(out); return rc; }
+    out->nnodes[l] = nn;
+    if (l <= N - 3) {
+      // +1 pad so a one-past-the-end prefetch stays in bounds
+      void * up = nullptr;
+      cudaError_t e = cudaMalloc(&up, (nn + 1) * 4);
+      if (e != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+      cudaMemset(up, 0, (nn + 1) * 4);
+      out->up[l] = static_cast<uint32_t *>(up);
+      held += (nn + 1) * 4;
+      if (nnz) {
+        k_scatter_nodes<<<nblk(nnz), 256>>>(sc.dl.as<uint8_t>(), l, nid.as<uint32_t>(),
+                                            sc.sidx[l].as<uint32_t>(), nnz, out->up[l], nullptr,
+                                            nullptr, nullptr);
+        if (out->nchunks)
+          k_desc<<<nblk(out->nchunks), 256>>>(nid.as<uint32_t>(), nnz, c0, out->nchunks, l, stride,
+                                              desc.as<uint32_t>());
+      }
+    }
+  }
+  out->nnodes[N - 1] = nnz;
+  {
+    void * rec = nullptr;
+    cudaError_t e = cudaMalloc(&rec, std::max<uint64_t>(out->nrec, 1) * sizeof(SpRec));
+    if (e != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+    out->rec = static_cast<SpRec *>(rec);
+    held += out->nrec * sizeof(SpRec);
+    if (out->nrec)
+      k_fill_rec<<<nblk(out->nrec), 256>>>(d_vals, sc.order_ptr(), sc.sidx[N - 1].as<uint32_t>(),
+                                           sc.sidx[N - 2].as<uint32_t>(), sc.dl.as<uint8_t>(), N,
+                                           nnz, r0, out->nrec, out->rec);
+  }
+  held += desc.bytes;
+  out->desc = static_cast<uint32_t *>(desc.release());
+  out->bytes = held;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return SPLATT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// Reference-shaped host CSF (one tile, untiled) from device COO.
+// Mirrors what p_csf_alloc_untiled builds (reference: src/csf.c:468-502):
+//   fids[N-1] = sorted leaf indices, vals = sorted values,
+//   for l < N-1: fids[l][f] / fptr[l][f] per node, fptr[l][nfibs] = #children
+//   level; fids[0] == NULL iff every root index occurs (src/csf.c:303-309).
+// ---------------------------------------------------------------------------
+static splatt_idx_t * widen_to_host(const uint32_t * d, uint64_t n, uint64_t extra_slots) {
+  std::vector<uint32_t> h(n ? n : 1);
+  if (n && cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+  splatt_idx_t * o = static_cast<splatt_idx_t *>(malloc((n + extra_slots + 1) * sizeof(splatt_idx_t)));
+  if (!o) return nullptr;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) o[i] = h[i];
+  return o;
+}
+
+int spb200_build_host_csf(int N, const uint64_t * dims, uint64_t nnz,
+                          const uint32_t * const * d_ind, const double * d_vals, const int * perm,
+                          splatt_csf * csf) {
+  memset(csf, 0, sizeof(*csf));
+  csf->nnz = nnz;
+  csf->nmodes = N;
+  for (int m = 0; m < N; ++m) {
+    csf->dims[m] = dims[m];
+    csf->dim_perm[m] = perm[m];
+    csf->dim_iperm[perm[m]] = m;
+    csf->tile_dims[m] = 1;
+  }
+  csf->which_tile = SPLATT_NOTILE;
+  csf->ntiles = 1;
+  csf->ntiled_modes = 0;
+  csf->pt = static_cast<csf_sparsity *>(calloc(1, sizeof(csf_sparsity)));
+  if (!csf->pt) return SPLATT_ERROR_NOMEMORY;
+  csf_sparsity * pt = csf->pt;
+
+  SortedCoo sc;
+  int rc = sort_coo(N, dims, nnz, d_ind, perm, false, &sc);
+  if (rc != SPLATT_SUCCESS) return rc;
+
+  // leaves
+  pt->nfibs[N - 1] = nnz;
+  pt->fids[N - 1] = widen_to_host(sc.sidx[N - 1].as<uint32_t>(), nnz, 0);
+  pt->vals = static_cast<splatt_val_t *>(malloc((nnz + 1) * sizeof(double)));
+  if (!pt->fids[N - 1] || !pt->vals) return SPLATT_ERROR_NOMEMORY;
+  {
+    DevBuf sv;
+    CK(sv.alloc(nnz * 8));
+    if (nnz) {
+      k_gather_f64<<<nblk(nnz), 256>>>(d_vals, sc.order_ptr(), nnz, sv.as<double>());
+      CK(cudaMemcpy(pt->vals, sv.p, nnz * 8, cudaMemcpyDeviceToHost));
+    }
+  }
+
+  DevBuf flag, nid, nid_child, tmp, ids, starts;
+  CK(flag.alloc(nnz * 4));
+  CK(nid.alloc(nnz * 4));
+  CK(nid_child.alloc(nnz * 4));
+  CK(ids.alloc(nnz * 4));
+  CK(starts.alloc(nnz * 4));
+  uint64_t nn_child = nnz;
+  for (int l = N - 2; l >= 0; --l) {
+    uint64_t nn = 0;
+    rc = scan_level(sc, l, flag, nid, tmp, &nn);
+    if (rc != SPLATT_SUCCESS) return rc;
+    if (nnz) {
+      // fptr[l][f]: for l == N-2 the leaf position, else the child node number
+      k_scatter_nodes<<<nblk(nnz), 256>>>(
+          sc.dl.as<uint8_t>(), l, nid.as<uint32_t>(), sc.sidx[l].as<uint32_t>(), nnz,
+          ids.as<uint32_t>(), (l == N - 2) ? starts.as<uint32_t>() : nullptr,
+          (l == N - 2) ? nullptr : nid_child.as<uint32_t>(),
+          (l == N - 2) ? nullptr : starts.as<uint32_t>());
+      CK(cudaGetLastError());
+    }
+    pt->nfibs[l] = nn;
+    pt->fids[l] = widen_to_host(ids.as<uint32_t>(), nn, 0);
+    pt->fptr[l] = widen_to_host(starts.as<uint32_t>(), nn, 1);
+    if (!pt->fids[l] || !pt->fptr[l]) return SPLATT_ERROR_NOMEMORY;
+    pt->fptr[l][nn] = nn_child;
+    nn_child = nn;
+    std::swap(nid.p, nid_child.p);
+  }
+  // root ids are implicit when the root mode has no empty slices
+  if (pt->nfibs[0] == dims[perm[0]]) {
+    free(pt->fids[0]);
+    pt->fids[0] = nullptr;
+  }
+  return SPLATT_SUCCESS;
+}

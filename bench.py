@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- MTTKRP nnz*R/sec per mode on synthetic sparse tensors (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one MTTKRP sweep: one MTTKRP per mode of the tensor (the hot path of
+one CPD-ALS iteration).  value = nnz_total * R * nmodes / step time = the mean
+per-mode throughput, whole-job aggregate over all ranks.
+
+Workload (config.workload): BASELINE.json configs[1] at N=1 -- synthetic uniform
+3-mode 10K x 10K x 10K, 10M nonzeros, rank 32, fp64.  For N>1 the per-GPU work is
+held fixed (weak scaling): the tensor has 10M*N nonzeros in the same 10K^3 index
+space, every rank holds an equal-nnz contiguous share of each mode's fiber
+stream (slices split at share boundaries), computes a partial output and the
+ranks sum it with one NCCL all-reduce per mode -- the north star's exchange step.
+
+Timed region: inputs resident in HBM; per step CUDA events on the launching
+stream; L2 flushed (256 MB write) between steps, outside the events; MAX over
+ranks.  `e2e` is the same sweep through the reference-facing C-ABI call
+(splatt_mttkrp_csf with a workspace) with pinned HOST buffers: H2D of the
+factors and D2H of the result inside the timed region.
+
+`--impl reference` times the reference's own OpenMP mttkrp_csf (oracle/_ref,
+compiled unmodified from /root/reference) on the host cores on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DIM = 10_000
+NNZ_PER_GPU = 10_000_000
+RANK = 32
+NMODES = 3
+SEED = 1
+FALLBACK_HBM_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- workload
+def make_coo_gpu(nnz: int, device):
+    import torch
+    g = torch.Generator(device=device).manual_seed(SEED)
+    ind = [torch.randint(0, DIM, (nnz,), device=device, dtype=torch.int32, generator=g)
+           for _ in range(NMODES)]
+    vals = torch.rand(nnz, device=device, dtype=torch.float64, generator=g)
+    return ind, vals
+
+
+def make_factors_host(seed=SEED):
+    rng = np.random.default_rng(1000 + seed)
+    return [np.ascontiguousarray(rng.uniform(-3.0, 3.0, size=(DIM, RANK))) for _ in range(NMODES)]
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------- reference arm
+def reference_sweeps(ind_host, vals_host, mats, steps, warmup, nthreads=None):
+    """Time the reference's mttkrp_csf (ws/thds allocated once per mode call group)."""
+    from oracle import ref
+    o = ref.default_opts()
+    if nthreads:
+        o[0] = nthreads
+    cores = int(o[0])
+    dims = [DIM] * NMODES
+    t0 = time.time()
+    tt = ref.RefTensor.from_coo(dims, ind_host, vals_host)
+    csf = ref.RefCsf(tt, o)         # reference csf_alloc: default TWOMODE, untiled
+    log(f"[reference] csf_alloc {time.time()-t0:.1f}s, {cores} threads")
+    per_mode = []
+    for m in range(NMODES):
+        _, times = csf.mttkrp_csf(mats, m, warm=warmup, iters=steps)
+        per_mode.append(times)
+    step_s = np.sum(np.stack(per_mode), axis=0)         # per-step sweep time
+    csf.free()
+    tt.free()
+    return step_s, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    try:
+        from oracle import ref
+        if not ref.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built"}))
+            return 0
+        import torch
+        nnz = NNZ_PER_GPU * max(args.gpus, 1)
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        ind, vals = make_coo_gpu(nnz, dev)
+        ind_h = [i.cpu().numpy().astype(np.uint64) for i in ind]
+        vals_h = vals.cpu().numpy()
+        del ind, vals
+        mats = make_factors_host()
+        step_s, cores = reference_sweeps(ind_h, vals_h, mats, args.steps, args.warmup)
+        ms = float(np.mean(step_s) * 1e3)
+        value = nnz * RANK * NMODES / (ms * 1e-3)
+        line = {"metric": "MTTKRP nnz*R/sec per mode", "value": value, "unit": "nnz*R/s",
+                "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args.gpus),
+                "cpu_baseline": {"value": value, "unit": "nnz*R/s", "cores": cores,
+                                 "kind": "reference",
+                                 "sample": f"full workload, {args.steps} sweeps x {NMODES} modes, "
+                                           "reference mttkrp_csf (OpenMP, TWOMODE, untiled)"},
+                "e2e": {"value": value, "unit": "nnz*R/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+    except Exception as e:  # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": f"synthetic uniform 3-mode {DIM}^3, {NNZ_PER_GPU} nnz per GPU "
+                        f"({NNZ_PER_GPU * max(n_gpus,1)} total), rank {RANK} "
+                        "(BASELINE.json configs[1] at N=1)",
+            "dims": [DIM] * NMODES, "nnz_total": NNZ_PER_GPU * max(n_gpus, 1), "rank": RANK,
+            "step": "one MTTKRP per mode (3 launches + N>1: 3 all-reduces)",
+            "partition": "equal-nnz contiguous shares of every mode's fiber stream; "
+                         "NCCL all-reduce(sum) of the output factor per mode",
+            "l2": "flushed between steps (256 MB write, outside the timed events)",
+            "seed": SEED}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import splatt_b200 as S
+    from splatt_b200 import _abi as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the CUDA extension is the product, "
+                           "there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    nnz_total = NNZ_PER_GPU * n_gpus
+    dims = [DIM] * NMODES
+
+    # ---- build: identical tensor on every rank, each keeps its share of every stream
+    ind, vals = make_coo_gpu(nnz_total, dev)
+    t0 = time.time()
+    T = S.Tensor.from_coo(dims, ind, vals, layout=A.LAYOUT_ALLROOT, shard_rank=rank,
+                          shard_count=world)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    mats_h = make_factors_host()
+    mats = [torch.from_numpy(m).to(dev) for m in mats_h]
+    outs = [torch.empty((dims[m], RANK), dtype=torch.float64, device=dev) for m in range(NMODES)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    info = [T.mode_info(m, RANK) for m in range(NMODES)]
+
+    def sweep(events=None):
+        for m in range(NMODES):
+            if events is not None:
+                events[m][0].record()
+            T.mttkrp(m, mats, outs[m])
+            if events is not None:
+                events[m][1].record()
+            if world > 1:
+                dist.all_reduce(outs[m])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        sweep()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = S.launch_count()
+    step_ms, kern_ms = [], [[] for _ in range(NMODES)]
+    wall0 = time.time()
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        ke = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(NMODES)]
+        e0.record()
+        sweep(ke)
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        for m in range(NMODES):
+            kern_ms[m].append(ke[m][0].elapsed_time(ke[m][1]))
+    barrier()
+    wall_s = time.time() - wall0
+    launches = S.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = nnz_total * RANK * NMODES / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the public call
+    e2e_ms = None
+    h2d = sum(dims[o] * RANK * 8 for m in range(NMODES) for o in range(NMODES) if o != m)
+    d2h = sum(dims[m] * RANK * 8 for m in range(NMODES))
+    pin = [torch.from_numpy(m).pin_memory() for m in mats_h]
+    pout = [torch.empty((dims[m], RANK), dtype=torch.float64).pin_memory() for m in range(NMODES)]
+    if world == 1:
+        # reference-facing C ABI: splatt_mttkrp_alloc_ws once, splatt_mttkrp_csf per mode
+        ind_h = [i.cpu().numpy() for i in ind]
+        vals_h = vals.cpu().numpy()
+        o = S.default_opts()
+        csf = S.csf_alloc(dims, ind_h, vals_h, o)
+        ws = S.MttkrpWorkspace(csf.ptr, RANK, o)
+        pin_np = [p.numpy() for p in pin]
+        pout_np = [p.numpy() for p in pout]
+
+        def e2e_sweep():
+            for m in range(NMODES):
+                ws.mttkrp_csf(pin_np, m, pout_np[m])      # H2D + kernel + D2H + sync inside
+    else:
+        def e2e_sweep():
+            for m in range(NMODES):
+                dm = [None if o == m else pin[o].to(dev, non_blocking=True) for o in range(NMODES)]
+                for o in range(NMODES):
+                    if o != m:
+                        mats[o].copy_(dm[o])
+                T.mttkrp(m, mats, outs[m])
+                dist.all_reduce(outs[m])
+                pout[m].copy_(outs[m], non_blocking=True)
+            torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_sweep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_sweep()
+    barrier()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item()) * 1e3
+    e2e_value = nnz_total * RANK * NMODES / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        # roofline of the dominant kernel: the root-stream kernel of mode 0
+        peak, how = hbm_peak()
+        k_ms = float(np.mean(kern_ms[0]))
+        alg = info[0]["alg_bytes"]
+        achieved = alg / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "mttkrp_stream_kernel<3,16,root> (mode 0)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": how, "alg_bytes_per_launch": alg,
+                "launch_ms": k_ms, "traffic": ncu_traffic(),
+                "per_mode_ms": [float(np.mean(k)) for k in kern_ms],
+                "kernel_share_of_step": float(sum(np.mean(k) for k in kern_ms) / ms_per_step),
+                "note": "alg bytes = 16 B/nnz record stream + 4 B/node upper-level ids + "
+                        "3 factor-sized matrices (2 read, 1 written); SURVEY 8(d) at stored widths"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    ind_h64 = [i.cpu().numpy().astype(np.uint64) for i in ind]
+                    step_s, cores = reference_sweeps(ind_h64, vals.cpu().numpy(), mats_h, 3, 1)
+                    cv = nnz_total * RANK * NMODES / float(np.mean(step_s))
+                    cpu = {"value": cv, "unit": "nnz*R/s", "cores": cores, "kind": "reference",
+                           "sample": "full workload: 3 sweeps x 3 modes after 1 warm-up, reference "
+                                     "mttkrp_csf (OpenMP, TWOMODE, untiled, all host threads)"}
+                else:
+                    cpu = {"value": None, "unit": "nnz*R/s", "cores": 0, "kind": "reference",
+                           "sample": "oracle/_ref not present"}
+            except Exception as e:  # pragma: no cover
+                cpu = {"value": None, "unit": "nnz*R/s", "cores": 0, "kind": "reference",
+                       "sample": f"failed: {e}"}
+        line = {"metric": "MTTKRP nnz*R/sec per mode", "value": value, "unit": "nnz*R/s",
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(n_gpus),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "nnz*R/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "path": "splatt_mttkrp_csf (C ABI, pinned host buffers)" if world == 1
+                                else "Tensor.mttkrp + NCCL all-reduce with pinned host buffers"},
+                "gpu_launches": int(launches),
+                "roofline": roof,
+                "cpu_baseline": cpu,
+                "build_seconds": build_s, "wall_seconds_timed_region": wall_s,
+                "device_bytes": T.device_bytes}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

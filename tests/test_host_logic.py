@@ -1,0 +1,55 @@
+"""CPU: host-side logic of the engine that needs no GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import restate
+from splatt_b200 import _abi as A
+
+DIMS = [[30, 10, 20], [10, 10, 10], [30, 10, 20, 10], [5, 4, 3, 2, 1], [7, 7, 3, 7, 3, 9],
+        [2425, 10816, 29567], [60114, 83826, 23034, 1132, 100], [4, 3, 5, 4, 3, 6, 2, 5]]
+
+
+def level_orders(lib, dims, alloc):
+    d = np.ascontiguousarray(dims, dtype=np.uint64)
+    perms = (C.c_int * 64)()
+    mp = (C.c_int * 8)()
+    n = lib.splatt_b200_level_orders(d.ctypes.data_as(A.idx_p), len(dims), alloc, perms, mp)
+    return [[perms[c * 8 + l] for l in range(len(dims))] for c in range(n)], [mp[m] for m in
+                                                                             range(len(dims))]
+
+
+@pytest.mark.parametrize("dims", DIMS)
+@pytest.mark.parametrize("alloc", [0, 1, 2])
+def test_level_orders_match_restatement(lib, dims, alloc):
+    assert level_orders(lib, dims, alloc) == restate.csf_policy(dims, alloc)
+
+
+@pytest.mark.parametrize("dims", DIMS)
+def test_level_orders_match_compiled_reference(lib, refmod, dims):
+    """csf_find_mode_order (src/csf.c:694-726) for the orders csf_alloc uses (:770-814)."""
+    n = len(dims)
+    small = refmod.mode_order(dims, refmod.CSF_SORTED_SMALLFIRST)
+    assert level_orders(lib, dims, 0)[0] == [small]
+    two, mp = level_orders(lib, dims, 1)
+    assert two[0] == small
+    assert two[1] == refmod.mode_order(dims, refmod.CSF_SORTED_MINUSONE, small[-1])
+    assert mp == [1 if m == small[-1] else 0 for m in range(n)]
+    allm, mp = level_orders(lib, dims, 2)
+    assert allm == [refmod.mode_order(dims, refmod.CSF_SORTED_MINUSONE, m) for m in range(n)]
+    assert mp == list(range(n))
+    for which in range(4):
+        assert restate.mode_order(dims, which, n - 1) == refmod.mode_order(dims, which, n - 1)
+
+
+def test_bad_policy_is_rejected(lib):
+    assert level_orders(lib, [3, 4, 5], 7) == ([], [0, 0, 0])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: a missing extension is an error, not a slow path."""
+    monkeypatch.setattr(A, "_lib", None)
+    monkeypatch.setattr(A, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(RuntimeError, match="no fallback"):
+        A.load()

@@ -6,11 +6,13 @@
 #error "compile with -DSPB200_INST_N=<nmodes>"
 #endif
 
+int spb200_root_batch();
+
 namespace spb200 {
 
-template <int N, int L, int KIND>
+template <int N, int L, int KIND, int BATCH>
 static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
-  auto kern = mttkrp_stream_kernel<N, L, KIND>;
+  auto kern = mttkrp_stream_kernel<N, L, KIND, BATCH>;
   static int occ = 0;   // per-variant, set once
   if (occ == 0) {
     SPB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -34,9 +36,11 @@ static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t str
 template <int N, int L>
 static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
   switch (kind) {
-    case SPB200_KIND_ROOT: return launch_variant<N, L, SPB200_KIND_ROOT>(args, num_sms, stream);
-    case SPB200_KIND_INTL: return launch_variant<N, L, SPB200_KIND_INTL>(args, num_sms, stream);
-    default:               return launch_variant<N, L, SPB200_KIND_LEAF>(args, num_sms, stream);
+    case SPB200_KIND_ROOT:
+      if (spb200_root_batch() >= 8) return launch_variant<N, L, SPB200_KIND_ROOT, 8>(args, num_sms, stream);
+      return launch_variant<N, L, SPB200_KIND_ROOT, 4>(args, num_sms, stream);
+    case SPB200_KIND_INTL: return launch_variant<N, L, SPB200_KIND_INTL, 4>(args, num_sms, stream);
+    default:               return launch_variant<N, L, SPB200_KIND_LEAF, 4>(args, num_sms, stream);
   }
 }
 

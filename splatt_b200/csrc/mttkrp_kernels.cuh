@@ -36,7 +36,6 @@ constexpr int kThreads   = 256;
 constexpr int kWarps     = kThreads / 32;
 constexpr int kStageRecs = 128;   // records per warp per stage (2 KB)
 constexpr int kStages    = 3;
-constexpr int kBatch     = 4;     // records whose gathers are issued together
 
 constexpr size_t kSmemBytes =
     sizeof(SpRec) * kWarps * kStages * kStageRecs + sizeof(uint64_t) * kWarps * kStages;
@@ -77,13 +76,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void * dst, const void * src, uint3
       : "memory");
 }
 
-__device__ __forceinline__ double2 ld_row(const double * __restrict__ base, uint32_t idx, int ldm,
-                                          int col) {
-  return __ldg(reinterpret_cast<const double2 *>(base + static_cast<size_t>(idx) * ldm + col));
+// Row addressing: `base` already points at this lane's column pair; the row offset
+// is one 32x32->64 multiply-add (IMAD.WIDE.U32) of the index with the row pitch.
+__device__ __forceinline__ double2 ld_row(const char * __restrict__ base, uint32_t idx,
+                                          uint32_t pitch) {
+  return __ldg(reinterpret_cast<const double2 *>(base + static_cast<uint64_t>(idx) * pitch));
 }
-__device__ __forceinline__ void red_row(double * __restrict__ base, uint32_t idx, int ldm, int col,
+__device__ __forceinline__ void red_row(char * __restrict__ base, uint32_t idx, uint32_t pitch,
                                         double2 x) {
-  double * p = base + static_cast<size_t>(idx) * ldm + col;
+  double * p = reinterpret_cast<double *>(base + static_cast<uint64_t>(idx) * pitch);
   atomicAdd(p, x.x);      // result unused -> RED.E.ADD.F64
   atomicAdd(p + 1, x.y);
 }
@@ -97,26 +98,59 @@ __device__ __forceinline__ double2 mul2(double2 a, double2 b) {
   return make_double2(a.x * b.x, a.y * b.y);
 }
 
-template <int N, int L, int KIND>
-__global__ void __launch_bounds__(kThreads, 2) mttkrp_stream_kernel(const MttkrpArgs a) {
+// One record of the root traversal (levels above the leaf fold upwards; the
+// root row leaves the SM with a RED).  `b`/`r` are the gathered leaf / parent rows.
+template <int N>
+__device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q, const double2 b,
+                                            const double2 r, double2 (&acc)[N - 1],
+                                            uint32_t (&pos)[N - 2], const char * const (&mbase)[N],
+                                            char * obase, uint32_t pitch) {
+  const double2  zero2 = make_double2(0.0, 0.0);
+  const double   v     = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+  const uint32_t c     = q.w >> SPB200_IDX_BITS;
+  acc[N - 2]           = fma2(v, b, acc[N - 2]);
+  if (c) {
+    acc[N - 3] = fma2(acc[N - 2], r, acc[N - 3]);
+    acc[N - 2] = zero2;
+    if (c >= 2) {
+#pragma unroll
+      for (int l = N - 3; l >= 1; --l) {
+        if (c >= uint32_t(N - 1 - l)) {
+          const uint32_t idx = __ldg(&a.up[l][pos[l]]);
+          ++pos[l];
+          acc[l - 1] = fma2(acc[l], ld_row(mbase[l], idx, pitch), acc[l - 1]);
+          acc[l]     = zero2;
+        }
+      }
+      if (c >= uint32_t(N - 1)) {
+        const uint32_t row = __ldg(&a.up[0][pos[0]]);
+        ++pos[0];
+        red_row(obase, row, pitch, acc[0]);
+        acc[0] = zero2;
+      }
+    }
+  }
+}
+
+template <int N, int L, int KIND, int BATCH>
+__global__ void __launch_bounds__(kThreads, (BATCH >= 8 ? 2 : 3))
+mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
   constexpr int G  = 32 / L;            // groups per warp
   constexpr int SU = kStageRecs / G;    // records per group per stage
-  static_assert(SU % kBatch == 0, "stage must hold whole batches");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpRec *    srec = reinterpret_cast<SpRec *>(smem_raw);
   uint64_t * bars =
       reinterpret_cast<uint64_t *>(smem_raw + sizeof(SpRec) * kWarps * kStages * kStageRecs);
 
-  const int  warp   = threadIdx.x >> 5;
-  const int  lane   = threadIdx.x & 31;
-  const int  grp    = lane / L;
-  const int  gl     = lane % L;
-  const bool act    = (2 * gl) < a.ncols;
-  const bool leader = (gl == 0);
-  const int  col    = a.col0 + 2 * gl;
-  const int  ldm    = a.ldm;
+  const int      warp   = threadIdx.x >> 5;
+  const int      lane   = threadIdx.x & 31;
+  const int      grp    = lane / L;
+  const int      gl     = lane % L;
+  const bool     act    = (2 * gl) < a.ncols;   // lanes past the last column only keep the warp in step
+  const bool     leader = (gl == 0);
+  const uint32_t pitch  = static_cast<uint32_t>(a.ldm) * 8u;
 
   if (lane == 0) {
 #pragma unroll
@@ -155,6 +189,13 @@ __global__ void __launch_bounds__(kThreads, 2) mttkrp_stream_kernel(const Mttkrp
     }
   };
 
+  // Per-lane matrix bases (already offset to this lane's column pair), by level.
+  const int    colx = act ? (a.col0 + 2 * gl) : a.col0;
+  const char * mbase[N];
+#pragma unroll
+  for (int l = 0; l < N; ++l) mbase[l] = reinterpret_cast<const char *>(a.mats[l] + colx);
+  char * obase = reinterpret_cast<char *>(a.out + colx);
+
   // Traversal state.
   const double2 zero2 = make_double2(0.0, 0.0);
   double2       acc[N - 1];   // partial sums of levels 0..N-2 (levels >= outdepth)
@@ -183,129 +224,126 @@ __global__ void __launch_bounds__(kThreads, 2) mttkrp_stream_kernel(const Mttkrp
       buf[cnt - 1].aux = (buf[cnt - 1].aux & SPB200_IDX_MASK) | (uint32_t(N - 1) << SPB200_IDX_BITS);
     __syncwarp();
 
-    if constexpr (KIND == SPB200_KIND_ROOT) {
-      for (uint32_t n0 = 0; n0 < cnt; n0 += kBatch) {
-        uint4   q[kBatch];
-        double2 b[kBatch], r[kBatch];
+    if (act) {
+      if constexpr (KIND == SPB200_KIND_ROOT) {
+        uint32_t n0 = 0;
+        // full batches: all gathers of BATCH records are in flight before the first FMA
+        for (; n0 + BATCH <= cnt; n0 += BATCH) {
+          uint4   q[BATCH];
+          double2 b[BATCH], r[BATCH];
+          uint32_t any = 0;
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          q[u] = (n0 + u < cnt) ? *reinterpret_cast<const uint4 *>(&buf[n0 + u])
-                                : make_uint4(0u, 0u, 0u, 0u);
+          for (int u = 0; u < BATCH; ++u) {
+            q[u] = *reinterpret_cast<const uint4 *>(&buf[n0 + u]);
+            any |= q[u].w;
+          }
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          b[u] = (act && n0 + u < cnt) ? ld_row(a.mats[N - 1], q[u].z, ldm, col) : zero2;
+          for (int u = 0; u < BATCH; ++u) b[u] = ld_row(mbase[N - 1], q[u].z, pitch);
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          r[u] = (act && (q[u].w >> SPB200_IDX_BITS))
-                     ? ld_row(a.mats[N - 2], q[u].w & SPB200_IDX_MASK, ldm, col)
-                     : zero2;
+          for (int u = 0; u < BATCH; ++u)
+            if (q[u].w >> SPB200_IDX_BITS) r[u] = ld_row(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch);
+          if ((any >> (SPB200_IDX_BITS + 1)) == 0) {
+            // common case: no record of the batch closes more than its fiber --
+            // straight-line, predicated, no branches
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const double   v = __hiloint2double(static_cast<int>(q[u].y), static_cast<int>(q[u].x));
-          const uint32_t c = q[u].w >> SPB200_IDX_BITS;
-          acc[N - 2]       = fma2(v, b[u], acc[N - 2]);
+            for (int u = 0; u < BATCH; ++u) {
+              const double v = __hiloint2double(static_cast<int>(q[u].y), static_cast<int>(q[u].x));
+              acc[N - 2]     = fma2(v, b[u], acc[N - 2]);
+              if (q[u].w >> SPB200_IDX_BITS) {
+                acc[N - 3] = fma2(acc[N - 2], r[u], acc[N - 3]);
+                acc[N - 2] = zero2;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+              root_record<N>(a, q[u], b[u], r[u], acc, pos, mbase, obase, pitch);
+          }
+        }
+        for (; n0 < cnt; ++n0) {   // tail of the range's last stage
+          const uint4   q = *reinterpret_cast<const uint4 *>(&buf[n0]);
+          const double2 b = ld_row(mbase[N - 1], q.z, pitch);
+          double2       r = zero2;
+          if (q.w >> SPB200_IDX_BITS) r = ld_row(mbase[N - 2], q.w & SPB200_IDX_MASK, pitch);
+          root_record<N>(a, q, b, r, acc, pos, mbase, obase, pitch);
+        }
+      } else if constexpr (KIND == SPB200_KIND_INTL) {
+#pragma unroll 2
+        for (uint32_t n = 0; n < cnt; ++n) {
+          const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
+          const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+          const uint32_t c   = q.w >> SPB200_IDX_BITS;
+          const uint32_t par = q.w & SPB200_IDX_MASK;
+          const double2  b   = ld_row(mbase[N - 1], q.z, pitch);
+          // (re)open prefix levels that changed after the previous record
+          if (pc >= uint32_t(N - d)) {
+#pragma unroll
+            for (int l = 0; l <= N - 3; ++l) {
+              if (l < d && l + int(pc) >= N - 1) {
+                const uint32_t idx = __ldg(&a.up[l][pos[l]]);
+                const double2  row = ld_row(mbase[l], idx, pitch);
+                pre[l]             = (l == 0) ? row : mul2(pre[l - 1], row);
+              }
+            }
+          }
+          acc[N - 2] = fma2(v, b, acc[N - 2]);
           if (c) {
-            acc[N - 3] = fma2(acc[N - 2], r[u], acc[N - 3]);
-            acc[N - 2] = zero2;
-            if (c >= 2) {
+            // levels below the output level fold upwards
 #pragma unroll
-              for (int l = N - 3; l >= 1; --l) {
-                if (c >= uint32_t(N - 1 - l)) {
-                  const uint32_t idx = __ldg(&a.up[l][pos[l]]);
-                  ++pos[l];
-                  if (act) {
-                    const double2 row = ld_row(a.mats[l], idx, ldm, col);
-                    acc[l - 1]        = fma2(acc[l], row, acc[l - 1]);
-                  }
-                  acc[l] = zero2;
-                }
-              }
-              if (c >= uint32_t(N - 1)) {
-                const uint32_t row = __ldg(&a.up[0][pos[0]]);
-                ++pos[0];
-                if (act) red_row(a.out, row, ldm, col, acc[0]);
-                acc[0] = zero2;
+            for (int l = N - 2; l >= 2; --l) {
+              if (l > d && c >= uint32_t(N - 1 - l)) {
+                uint32_t idx;
+                if (l == N - 2) idx = par;
+                else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
+                acc[l - 1] = fma2(acc[l], ld_row(mbase[l], idx, pitch), acc[l - 1]);
+                acc[l]     = zero2;
               }
             }
+            // the output level itself
+#pragma unroll
+            for (int l = 1; l <= N - 2; ++l) {
+              if (l == d && c >= uint32_t(N - 1 - l)) {
+                uint32_t idx;
+                if (l == N - 2) idx = par;
+                else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
+                red_row(obase, idx, pitch, mul2(pre[l - 1], acc[l]));
+                acc[l] = zero2;
+              }
+            }
+            // prefix levels that ended: advance to their next node
+#pragma unroll
+            for (int l = 0; l <= N - 3; ++l)
+              if (l < d && c >= uint32_t(N - 1 - l)) ++pos[l];
           }
+          pc = c;
         }
-      }
-    } else if constexpr (KIND == SPB200_KIND_INTL) {
+      } else {   // KIND_LEAF
 #pragma unroll 2
-      for (uint32_t n = 0; n < cnt; ++n) {
-        const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
-        const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
-        const uint32_t c   = q.w >> SPB200_IDX_BITS;
-        const uint32_t par = q.w & SPB200_IDX_MASK;
-        const double2  b   = act ? ld_row(a.mats[N - 1], q.z, ldm, col) : zero2;
-        // (re)open prefix levels that changed after the previous record
-        if (pc >= uint32_t(N - d)) {
+        for (uint32_t n = 0; n < cnt; ++n) {
+          const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
+          const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+          const uint32_t c   = q.w >> SPB200_IDX_BITS;
+          const uint32_t par = q.w & SPB200_IDX_MASK;
+          if (pc) {
 #pragma unroll
-          for (int l = 0; l <= N - 3; ++l) {
-            if (l < d && l + int(pc) >= N - 1) {
-              const uint32_t idx = __ldg(&a.up[l][pos[l]]);
-              const double2  row = act ? ld_row(a.mats[l], idx, ldm, col) : zero2;
-              pre[l]             = (l == 0) ? row : mul2(pre[l - 1], row);
+            for (int l = 0; l <= N - 2; ++l) {
+              if (l + int(pc) >= N - 1) {
+                uint32_t idx;
+                if (l == N - 2) idx = par;
+                else idx = __ldg(&a.up[l][pos[l]]);
+                const double2 row = ld_row(mbase[l], idx, pitch);
+                pre[l]            = (l == 0) ? row : mul2(pre[l - 1], row);
+              }
             }
           }
-        }
-        acc[N - 2] = fma2(v, b, acc[N - 2]);
-        if (c) {
-          // levels below the output level fold upwards
+          red_row(obase, q.z, pitch, make_double2(v * pre[N - 2].x, v * pre[N - 2].y));
+          if (c) {
 #pragma unroll
-          for (int l = N - 2; l >= 2; --l) {
-            if (l > d && c >= uint32_t(N - 1 - l)) {
-              uint32_t idx;
-              if (l == N - 2) idx = par;
-              else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
-              if (act) acc[l - 1] = fma2(acc[l], ld_row(a.mats[l], idx, ldm, col), acc[l - 1]);
-              acc[l] = zero2;
-            }
+            for (int l = 0; l <= N - 3; ++l)
+              if (c >= uint32_t(N - 1 - l)) ++pos[l];
           }
-          // the output level itself
-#pragma unroll
-          for (int l = 1; l <= N - 2; ++l) {
-            if (l == d && c >= uint32_t(N - 1 - l)) {
-              uint32_t idx;
-              if (l == N - 2) idx = par;
-              else { idx = __ldg(&a.up[l][pos[l]]); ++pos[l]; }
-              if (act) red_row(a.out, idx, ldm, col, mul2(pre[l - 1], acc[l]));
-              acc[l] = zero2;
-            }
-          }
-          // prefix levels that ended: advance to their next node
-#pragma unroll
-          for (int l = 0; l <= N - 3; ++l)
-            if (l < d && c >= uint32_t(N - 1 - l)) ++pos[l];
+          pc = c;
         }
-        pc = c;
-      }
-    } else {   // KIND_LEAF
-#pragma unroll 2
-      for (uint32_t n = 0; n < cnt; ++n) {
-        const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
-        const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
-        const uint32_t c   = q.w >> SPB200_IDX_BITS;
-        const uint32_t par = q.w & SPB200_IDX_MASK;
-        if (pc) {
-#pragma unroll
-          for (int l = 0; l <= N - 2; ++l) {
-            if (l + int(pc) >= N - 1) {
-              uint32_t idx;
-              if (l == N - 2) idx = par;
-              else idx = __ldg(&a.up[l][pos[l]]);
-              const double2 row = act ? ld_row(a.mats[l], idx, ldm, col) : zero2;
-              pre[l]            = (l == 0) ? row : mul2(pre[l - 1], row);
-            }
-          }
-        }
-        if (act) red_row(a.out, q.z, ldm, col, make_double2(v * pre[N - 2].x, v * pre[N - 2].y));
-        if (c) {
-#pragma unroll
-          for (int l = 0; l <= N - 3; ++l)
-            if (c >= uint32_t(N - 1 - l)) ++pos[l];
-        }
-        pc = c;
       }
     }
 

@@ -1,7 +1,18 @@
 // Host-side dispatch of one MTTKRP over a fiber stream.
 #include "common.h"
+#include <cstdlib>
 
 unsigned long long g_spb200_launches = 0;
+
+// Tuning knob (experiments): records per gather batch of the root kernel.
+int spb200_root_batch() {
+  static int v = -1;
+  if (v < 0) {
+    const char * e = getenv("SPLATT_B200_BATCH");
+    v = (e && atoi(e) >= 8) ? 8 : 4;
+  }
+  return v;
+}
 
 namespace spb200 {
 int launch_n3(int, const MttkrpArgs &, int, cudaStream_t);

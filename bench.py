@@ -144,25 +144,42 @@ def ncu_traffic():
 
 # --------------------------------------------------------------------------- reference arm
 def reference_sweeps(ind_host, vals_host, mats, steps, warmup, nthreads=None):
-    """Time the reference's mttkrp_csf (ws/thds allocated once per mode call group)."""
+    """Time the reference's mttkrp_csf (ws/thds allocated once per group of calls).
+
+    The reference gets its best thread count: torchrun exports OMP_NUM_THREADS=1 and
+    more threads than physical cores hurts it, so unless SPLATT_REF_THREADS pins it we
+    time one sweep at aff, aff/2, aff/4, aff/8 threads (aff = CPUs this process may run
+    on) and keep the fastest."""
     from oracle import ref
     o = ref.default_opts()
-    if nthreads:
-        o[0] = nthreads
-    cores = int(o[0])
+    aff = len(os.sched_getaffinity(0))
     dims = [DIM] * NMODES
     t0 = time.time()
+    o[0] = aff
     tt = ref.RefTensor.from_coo(dims, ind_host, vals_host)
     csf = ref.RefCsf(tt, o)         # reference csf_alloc: default TWOMODE, untiled
-    log(f"[reference] csf_alloc {time.time()-t0:.1f}s, {cores} threads")
-    per_mode = []
-    for m in range(NMODES):
-        _, times = csf.mttkrp_csf(mats, m, warm=warmup, iters=steps)
-        per_mode.append(times)
-    step_s = np.sum(np.stack(per_mode), axis=0)         # per-step sweep time
+    log(f"[reference] csf_alloc {time.time()-t0:.1f}s with {aff} threads")
+
+    def sweep(threads, warm, iters):
+        oo = o.copy()
+        oo[0] = threads
+        per_mode = [csf.mttkrp_csf(mats, m, warm=warm, iters=iters, opts=oo)[1]
+                    for m in range(NMODES)]
+        return np.sum(np.stack(per_mode), axis=0)
+
+    env = os.environ.get("SPLATT_REF_THREADS")
+    if nthreads is None and env:
+        nthreads = int(env)
+    if nthreads is None:
+        cands = sorted({max(1, aff // d) for d in (1, 2, 4, 8)})
+        trial = {t: float(sweep(t, 1, 1)[0]) for t in cands}
+        nthreads = min(trial, key=trial.get)
+        log("[reference] sweep seconds by thread count: " +
+            ", ".join(f"{t}:{trial[t]:.3f}" for t in cands) + f" -> using {nthreads}")
+    step_s = sweep(nthreads, warmup, steps)
     csf.free()
     tt.free()
-    return step_s, cores
+    return step_s, int(nthreads)
 
 
 def run_reference(args):
@@ -398,7 +415,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -302,6 +302,16 @@ void splatt_b200_csf_free(splatt_csf * csf, int csf_alloc);
 int splatt_b200_level_orders(
     uint64_t const * dims, int nmodes, int csf_alloc, int * perms, int * mode_csf_map);
 
+/* Host logic, no GPU needed: the records [first, first+count) of a sorted stream
+ * of `nnz` nonzeros that shard `rank` of `count_shards` keeps (equal numbers of
+ * 64-record chunks, so shares differ by at most one chunk; slices may be split
+ * at a share boundary -- the all-reduce adds the two partial rows).  Plays the
+ * role of the reference's per-thread slice partition (csf_partition_1d,
+ * src/csf.c:854-872 -> partition_weighted, src/thread_partition.c:156-195) at
+ * the granularity a GPU needs. */
+void splatt_b200_shard_range(
+    uint64_t nnz, int rank, int count_shards, uint64_t * first, uint64_t * count);
+
 /* Enqueue one MTTKRP on `stream` (a cudaStream_t passed as void*; NULL =
  * default stream).  d_mats[m] are DEVICE pointers, row-major with leading
  * dimension ldm (>= ncolumns, even so rows are 16-byte aligned); d_mats[mode]

@@ -17,7 +17,20 @@ layout = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 
 g = torch.Generator(device="cuda").manual_seed(1)
 dims = [dim] * N
-ind = [torch.randint(0, dim, (nnz,), device="cuda", dtype=torch.int32, generator=g) for _ in range(N)]
+if len(sys.argv) > 6 and sys.argv[6] == "zipf":
+    # config-5 shape family: dim x dim x 1000, Zipf(1.0) on the two long modes
+    dims = [dim, dim, 1000]
+    N = 3
+    def zipf(d):
+        w = 1.0 / torch.arange(1, d + 1, device="cuda", dtype=torch.float64)
+        cdf = torch.cumsum(w / w.sum(), 0)
+        u = torch.rand(nnz, device="cuda", dtype=torch.float64, generator=g)
+        r = torch.searchsorted(cdf, u).clamp_(max=d - 1)
+        perm = torch.randperm(d, device="cuda", generator=g)
+        return perm[r].to(torch.int32)
+    ind = [zipf(dim), zipf(dim), torch.randint(0, 1000, (nnz,), device="cuda", dtype=torch.int32, generator=g)]
+else:
+    ind = [torch.randint(0, dim, (nnz,), device="cuda", dtype=torch.int32, generator=g) for _ in range(N)]
 vals = torch.rand(nnz, device="cuda", dtype=torch.float64, generator=g)
 t0 = time.time()
 T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=1, verbosity=3)

@@ -90,7 +90,7 @@ EXPORTS = [
     "splatt_b200_tensor_from_csf", "splatt_b200_tensor_from_coo", "splatt_b200_tensor_free",
     "splatt_b200_tensor_info", "splatt_b200_mode_info", "splatt_b200_csf_alloc",
     "splatt_b200_csf_free", "splatt_b200_mttkrp", "splatt_b200_launch_count",
-    "splatt_b200_version", "splatt_b200_level_orders",
+    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range",
 ]
 
 _lib = None
@@ -158,5 +158,7 @@ def load() -> C.CDLL:
     lib.splatt_b200_level_orders.restype = C.c_int
     lib.splatt_b200_level_orders.argtypes = [idx_p, C.c_int, C.c_int, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
+    lib.splatt_b200_shard_range.restype = None
+    lib.splatt_b200_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, idx_p, idx_p]
     _lib = lib
     return lib

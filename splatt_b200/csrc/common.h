@@ -102,6 +102,8 @@ struct MttkrpArgs {
     }                                                                          \
   } while (0)
 
+void spb200_shard_chunks(uint64_t nnz, int rank, int nshards, uint64_t * c0, uint64_t * c1);
+
 // stream_build.cu -----------------------------------------------------------
 // Build one stream from device COO (ind[m] uint32[nnz], vals) in level order
 // `perm`.  If `presorted`, the input is already lexicographically sorted in

@@ -55,6 +55,16 @@ void spb200_mode_csf_map(int N, int csf_alloc, const int perm0[SPB200_MAXN], int
   }
 }
 
+// Chunk range [c0, c1) of shard `rank`: equal chunk counts (+-1).
+void spb200_shard_chunks(uint64_t nnz, int rank, int nshards, uint64_t * c0, uint64_t * c1) {
+  const uint64_t nchunks = (nnz + SPB200_CHUNK - 1) / SPB200_CHUNK;
+  if (nshards < 1) nshards = 1;
+  if (rank < 0) rank = 0;
+  if (rank >= nshards) rank = nshards - 1;
+  *c0 = nchunks * (uint64_t)rank / (uint64_t)nshards;
+  *c1 = nchunks * (uint64_t)(rank + 1) / (uint64_t)nshards;
+}
+
 namespace {
 
 struct DevCoo {
@@ -444,6 +454,17 @@ int splatt_b200_level_orders(uint64_t const * dims, int nmodes, int csf_alloc, i
       for (int l = 0; l < SPB200_MAXN; ++l) perms[c * SPB200_MAXN + l] = l < nmodes ? p[c][l] : 0;
   if (mode_csf_map) spb200_mode_csf_map(nmodes, csf_alloc, p[0], mode_csf_map);
   return nc;
+}
+
+void splatt_b200_shard_range(uint64_t nnz, int rank, int count_shards, uint64_t * first,
+                             uint64_t * count) {
+  uint64_t c0, c1;
+  spb200_shard_chunks(nnz, rank, count_shards, &c0, &c1);
+  const uint64_t r0 = c0 * SPB200_CHUNK;
+  uint64_t r1 = c1 * SPB200_CHUNK;
+  if (r1 > nnz) r1 = nnz;
+  if (first) *first = r0;
+  if (count) *count = r1 > r0 ? r1 - r0 : 0;
 }
 
 uint64_t splatt_b200_launch_count(void) { return g_spb200_launches; }

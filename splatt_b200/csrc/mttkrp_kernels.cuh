@@ -99,12 +99,14 @@ __device__ __forceinline__ double2 mul2(double2 a, double2 b) {
 }
 
 // One record of the root traversal (levels above the leaf fold upwards; the
-// root row leaves the SM with a RED).  `b`/`r` are the gathered leaf / parent rows.
+// root row leaves the SM with a RED).  `b`/`r` are the gathered leaf / parent
+// rows; for N >= 4 `r2` is the gathered level-(N-3) row (valid when c >= 2).
 template <int N>
 __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q, const double2 b,
-                                            const double2 r, double2 (&acc)[N - 1],
-                                            uint32_t (&pos)[N - 2], const char * const (&mbase)[N],
-                                            char * obase, uint32_t pitch) {
+                                            const double2 r, const double2 r2,
+                                            double2 (&acc)[N - 1], uint32_t (&pos)[N - 2],
+                                            const char * const (&mbase)[N], char * obase,
+                                            uint32_t pitch) {
   const double2  zero2 = make_double2(0.0, 0.0);
   const double   v     = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
   const uint32_t c     = q.w >> SPB200_IDX_BITS;
@@ -113,13 +115,18 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
     acc[N - 3] = fma2(acc[N - 2], r, acc[N - 3]);
     acc[N - 2] = zero2;
     if (c >= 2) {
+      if constexpr (N >= 4) {
+        ++pos[N - 3];
+        acc[N - 4] = fma2(acc[N - 3], r2, acc[N - 4]);
+        acc[N - 3] = zero2;
 #pragma unroll
-      for (int l = N - 3; l >= 1; --l) {
-        if (c >= uint32_t(N - 1 - l)) {
-          const uint32_t idx = __ldg(&a.up[l][pos[l]]);
-          ++pos[l];
-          acc[l - 1] = fma2(acc[l], ld_row(mbase[l], idx, pitch), acc[l - 1]);
-          acc[l]     = zero2;
+        for (int l = N - 4; l >= 1; --l) {
+          if (c >= uint32_t(N - 1 - l)) {
+            const uint32_t idx = __ldg(&a.up[l][pos[l]]);
+            ++pos[l];
+            acc[l - 1] = fma2(acc[l], ld_row(mbase[l], idx, pitch), acc[l - 1]);
+            acc[l]     = zero2;
+          }
         }
       }
       if (c >= uint32_t(N - 1)) {
@@ -133,7 +140,7 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
 }
 
 template <int N, int L, int KIND, int BATCH>
-__global__ void __launch_bounds__(kThreads, (BATCH >= 8 ? 2 : 3))
+__global__ void __launch_bounds__(kThreads, ((BATCH >= 8 || N >= 4) ? 2 : 3))
 mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
   constexpr int G  = 32 / L;            // groups per warp
@@ -229,43 +236,69 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
         uint32_t n0 = 0;
         // full batches: all gathers of BATCH records are in flight before the first FMA
         for (; n0 + BATCH <= cnt; n0 += BATCH) {
-          uint4   q[BATCH];
-          double2 b[BATCH], r[BATCH];
-          uint32_t any = 0;
+          uint4    q[BATCH];
+          double2  b[BATCH], r[BATCH], r2[BATCH];
+          uint32_t hi = 0;
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
             q[u] = *reinterpret_cast<const uint4 *>(&buf[n0 + u]);
-            any |= q[u].w;
+            hi   = max(hi, q[u].w);
           }
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) b[u] = ld_row(mbase[N - 1], q[u].z, pitch);
 #pragma unroll
           for (int u = 0; u < BATCH; ++u)
             if (q[u].w >> SPB200_IDX_BITS) r[u] = ld_row(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch);
-          if ((any >> (SPB200_IDX_BITS + 1)) == 0) {
-            // common case: no record of the batch closes more than its fiber --
-            // straight-line, predicated, no branches
+          uint32_t p2 = 0;
+          if constexpr (N >= 4) {
+            // level N-3 closes are frequent on deep trees: their ids are the next
+            // entries of up[N-3]; fetch ids, then rows, for the whole batch
+            uint32_t idx2[BATCH];
+            p2 = pos[N - 3];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+              if ((q[u].w >> SPB200_IDX_BITS) >= 2u) { idx2[u] = __ldg(&a.up[N - 3][p2]); ++p2; }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+              if ((q[u].w >> SPB200_IDX_BITS) >= 2u) r2[u] = ld_row(mbase[N - 3], idx2[u], pitch);
+          }
+          constexpr uint32_t kFast = (N >= 4) ? 3u : 2u;   // close counts handled branch-free
+          if ((hi >> SPB200_IDX_BITS) < kFast) {
+            // common case: nothing above level N-3 (N-2 for 3 modes) ends in this
+            // batch -- straight-line, predicated, no branches
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) {
-              const double v = __hiloint2double(static_cast<int>(q[u].y), static_cast<int>(q[u].x));
-              acc[N - 2]     = fma2(v, b[u], acc[N - 2]);
-              if (q[u].w >> SPB200_IDX_BITS) {
+              const double   v = __hiloint2double(static_cast<int>(q[u].y), static_cast<int>(q[u].x));
+              const uint32_t c = q[u].w >> SPB200_IDX_BITS;
+              acc[N - 2]       = fma2(v, b[u], acc[N - 2]);
+              if (c) {
                 acc[N - 3] = fma2(acc[N - 2], r[u], acc[N - 3]);
                 acc[N - 2] = zero2;
               }
+              if constexpr (N >= 4) {
+                if (c >= 2u) {
+                  acc[N - 4] = fma2(acc[N - 3], r2[u], acc[N - 4]);
+                  acc[N - 3] = zero2;
+                }
+              }
             }
+            if constexpr (N >= 4) pos[N - 3] = p2;
           } else {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
-              root_record<N>(a, q[u], b[u], r[u], acc, pos, mbase, obase, pitch);
+              root_record<N>(a, q[u], b[u], r[u], r2[u], acc, pos, mbase, obase, pitch);
           }
         }
         for (; n0 < cnt; ++n0) {   // tail of the range's last stage
           const uint4   q = *reinterpret_cast<const uint4 *>(&buf[n0]);
           const double2 b = ld_row(mbase[N - 1], q.z, pitch);
-          double2       r = zero2;
+          double2       r = zero2, r2 = zero2;
           if (q.w >> SPB200_IDX_BITS) r = ld_row(mbase[N - 2], q.w & SPB200_IDX_MASK, pitch);
-          root_record<N>(a, q, b, r, acc, pos, mbase, obase, pitch);
+          if constexpr (N >= 4) {
+            if ((q.w >> SPB200_IDX_BITS) >= 2u)
+              r2 = ld_row(mbase[N - 3], __ldg(&a.up[N - 3][pos[N - 3]]), pitch);
+          }
+          root_record<N>(a, q, b, r, r2, acc, pos, mbase, obase, pitch);
         }
       } else if constexpr (KIND == SPB200_KIND_INTL) {
 #pragma unroll 2

@@ -265,10 +265,8 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
   if (rc != SPLATT_SUCCESS) return rc;
 
   // shard = contiguous, equal-count range of chunks
-  const uint64_t nchunks_total = (nnz + SPB200_CHUNK - 1) / SPB200_CHUNK;
-  if (shard_count < 1) shard_count = 1;
-  const uint64_t c0 = nchunks_total * (uint64_t)shard_rank / (uint64_t)shard_count;
-  const uint64_t c1 = nchunks_total * (uint64_t)(shard_rank + 1) / (uint64_t)shard_count;
+  uint64_t c0 = 0, c1 = 0;
+  spb200_shard_chunks(nnz, shard_rank, shard_count, &c0, &c1);
   const uint64_t r0 = c0 * SPB200_CHUNK;
   const uint64_t r1 = std::min<uint64_t>(c1 * SPB200_CHUNK, nnz);
   out->nchunks = c1 - c0;

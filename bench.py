@@ -231,6 +231,46 @@ def workload_config(n_gpus):
             "seed": SEED}
 
 
+def cpd_iteration_times(S, csf, ind, vals, mats_h):
+    """CPD-ALS seconds per iteration (the metric's second half): splatt_cpd_als of this
+    library (MTTKRP + dense tail on the device) vs the reference's, same tensor, rank and
+    iteration count; set-up is removed by differencing two iteration counts."""
+    out = {"rank": RANK, "ours_ms": None, "reference_ms": None}
+    try:
+        def ours(n):
+            o = S.default_opts()
+            o[3], o[1], o[4] = n, 0.0, 0
+            t0 = time.perf_counter()
+            S.cpd_als(csf.ptr, RANK, o, seed=SEED)
+            return time.perf_counter() - t0
+        ours(1)
+        out["ours_ms"] = (ours(22) - ours(2)) / 20 * 1e3
+    except Exception as e:  # pragma: no cover
+        out["ours_error"] = str(e)
+    try:
+        from oracle import ref
+        if ref.available():
+            o = ref.default_opts()
+            o[1], o[4] = 0.0, 0
+            o[0] = int(os.environ.get("SPLATT_REF_THREADS", "32"))
+            tt = ref.RefTensor.from_coo([DIM] * NMODES,
+                                        [i.cpu().numpy().astype(np.uint64) for i in ind],
+                                        vals.cpu().numpy())
+            rc = ref.RefCsf(tt, o)
+
+            def theirs(n):
+                oo = o.copy()
+                oo[3] = n
+                t0 = time.perf_counter()
+                rc.cpd_als(RANK, SEED, opts=oo)
+                return time.perf_counter() - t0
+            out["reference_ms"] = (theirs(3) - theirs(1)) / 2 * 1e3
+            out["reference_threads"] = int(o[0])
+    except Exception as e:  # pragma: no cover
+        out["reference_error"] = str(e)
+    return out
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -322,6 +362,7 @@ def run_ours(args):
     d2h = sum(dims[m] * RANK * 8 for m in range(NMODES))
     pin = [torch.from_numpy(m).pin_memory() for m in mats_h]
     pout = [torch.empty((dims[m], RANK), dtype=torch.float64).pin_memory() for m in range(NMODES)]
+    csf = None
     if world == 1:
         # reference-facing C ABI: splatt_mttkrp_alloc_ws once, splatt_mttkrp_csf per mode
         ind_h = [i.cpu().numpy() for i in ind]
@@ -390,6 +431,9 @@ def run_ours(args):
             except Exception as e:  # pragma: no cover
                 cpu = {"value": None, "unit": "nnz*R/s", "cores": 0, "kind": "reference",
                        "sample": f"failed: {e}"}
+        cpd = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpd = cpd_iteration_times(S, csf, ind, vals, mats_h)
         line = {"metric": "MTTKRP nnz*R/sec per mode", "value": value, "unit": "nnz*R/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -403,6 +447,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": roof,
                 "cpu_baseline": cpu,
+                "cpd_als_iteration": cpd,
                 "build_seconds": build_s, "wall_seconds_timed_region": wall_s,
                 "device_bytes": T.device_bytes}
         print(json.dumps(line))

@@ -232,6 +232,287 @@ double csf_frobsq(const splatt_csf * t) {   // reference: src/csf.c:817-851
   return norm;
 }
 
+
+// ---------------------------------------------------------------------------
+// Device-side ALS tail: the same five steps as the host
+// functions above, as small kernels on the MTTKRP stream, so that an iteration
+// needs no host<->device traffic except one tiny read-back for the fit.
+// ---------------------------------------------------------------------------
+
+// G(upper, row-major) += A^T A over a block of rows.  reference: mat_aTa src/matrix.c:414-455
+__global__ void k_gram(const double * __restrict__ A, unsigned long long I, int R, int lda,
+                       double * __restrict__ G) {
+  extern __shared__ double tile[];           // 32 rows x R
+  const int nent = R * (R + 1) / 2;
+  constexpr int kMaxPer = 34;                // R <= 128: ceil(8256 / 256) = 33
+  double acc[kMaxPer];
+  short  ep[kMaxPer], eq[kMaxPer];
+  int    mine = 0;
+  for (int e = threadIdx.x; e < nent && mine < kMaxPer; e += blockDim.x) {
+    int p = 0, rem = e;                      // e -> (p, q >= p), row-major upper triangle
+    while (rem >= R - p) { rem -= R - p; ++p; }
+    ep[mine] = (short)p; eq[mine] = (short)(p + rem); acc[mine] = 0.0; ++mine;
+  }
+  for (unsigned long long r0 = (unsigned long long)blockIdx.x * 32; r0 < I;
+       r0 += (unsigned long long)gridDim.x * 32) {
+    const int rows = (int)min((unsigned long long)32, I - r0);
+    for (int x = threadIdx.x; x < rows * R; x += blockDim.x)
+      tile[x] = A[(r0 + x / R) * lda + (x % R)];
+    __syncthreads();
+    for (int t = 0; t < mine; ++t) {
+      double a = acc[t];
+      for (int i = 0; i < rows; ++i) a = fma(tile[i * R + ep[t]], tile[i * R + eq[t]], a);
+      acc[t] = a;
+    }
+    __syncthreads();
+  }
+  for (int t = 0; t < mine; ++t) atomicAdd(&G[eq[t] + ep[t] * R], acc[t]);
+}
+
+// Normal matrix = Hadamard of the other modes' Grams; Cholesky in shared memory.
+// reference: p_form_gram src/matrix.c:29-83 + potrf :554.  info = 1 when not SPD; then P holds
+// the pseudo-inverse (the role of the GELSS fallback :566-603).
+__global__ void k_form_chol(const double * __restrict__ ata, int nmodes, int mode, int R,
+                            double * __restrict__ Lout, double * __restrict__ Pout,
+                            int * __restrict__ info) {
+  extern __shared__ double sm[];             // R*R working copy (+ R*R for the fallback)
+  double * a = sm;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  for (int x = threadIdx.x; x < R * R; x += blockDim.x) {
+    const int i = x / R, j = x % R;
+    const int p = min(i, j), q = max(i, j);  // Grams are stored upper (row-major)
+    double v = 1.0;
+    for (int m = 0; m < nmodes; ++m)
+      if (m != mode) v *= ata[(size_t)m * R * R + q + p * R];
+    a[x] = v;
+    Pout[x] = v;                             // keep the unfactored matrix for the fallback
+  }
+  __syncthreads();
+  for (int j = 0; j < R && !bad; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = a[j + j * R];
+      if (!(d > 0.0)) bad = 1; else a[j + j * R] = sqrt(d);
+    }
+    __syncthreads();
+    if (bad) break;
+    const double djj = a[j + j * R];
+    for (int i = j + 1 + threadIdx.x; i < R; i += blockDim.x) a[j + i * R] /= djj;
+    __syncthreads();
+    // trailing update of the lower triangle: a[i][k] -= L[i][j] * L[k][j], i >= k > j
+    const int rem = R - j - 1;
+    for (int x = threadIdx.x; x < rem * rem; x += blockDim.x) {
+      const int i = j + 1 + x / rem, k = j + 1 + x % rem;
+      if (k <= i) a[k + i * R] -= a[j + i * R] * a[j + k * R];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (!bad) {
+    for (int x = threadIdx.x; x < R * R; x += blockDim.x) Lout[x] = a[x];
+    if (threadIdx.x == 0) *info = 0;
+    return;
+  }
+  // not SPD: Jacobi eigen-decomposition -> pseudo-inverse (one thread; rare path)
+  if (threadIdx.x == 0) {
+    double * A2 = a;            // reuse as the working symmetric matrix
+    double * V  = sm + R * R;
+    for (int x = 0; x < R * R; ++x) { A2[x] = Pout[x]; V[x] = 0.0; }
+    for (int i = 0; i < R; ++i) V[i + i * R] = 1.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+      double off = 0;
+      for (int p = 0; p < R; ++p) for (int q = p + 1; q < R; ++q) off += A2[q + p * R] * A2[q + p * R];
+      if (off < 1e-300) break;
+      for (int p = 0; p < R; ++p)
+        for (int q = p + 1; q < R; ++q) {
+          const double apq = A2[q + p * R];
+          if (fabs(apq) < 1e-300) continue;
+          const double theta = (A2[q + q * R] - A2[p + p * R]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          for (int k = 0; k < R; ++k) {
+            const double akp = A2[p + k * R], akq = A2[q + k * R];
+            A2[p + k * R] = c * akp - sn * akq; A2[q + k * R] = sn * akp + c * akq;
+          }
+          for (int k = 0; k < R; ++k) {
+            const double apk = A2[k + p * R], aqk = A2[k + q * R];
+            A2[k + p * R] = c * apk - sn * aqk; A2[k + q * R] = sn * apk + c * aqk;
+          }
+          for (int k = 0; k < R; ++k) {
+            const double vkp = V[p + k * R], vkq = V[q + k * R];
+            V[p + k * R] = c * vkp - sn * vkq; V[q + k * R] = sn * vkp + c * vkq;
+          }
+        }
+    }
+    double dmax = 0;
+    for (int i = 0; i < R; ++i) dmax = fmax(dmax, fabs(A2[i + i * R]));
+    const double cut = dmax * 2.220446049250313e-16;
+    for (int x = 0; x < R * R; ++x) Pout[x] = 0.0;
+    for (int e = 0; e < R; ++e) {
+      const double d = A2[e + e * R];
+      if (fabs(d) <= cut) continue;
+      for (int i = 0; i < R; ++i)
+        for (int j = 0; j < R; ++j) Pout[j + i * R] += V[e + i * R] * V[e + j * R] / d;
+    }
+    *info = 1;
+  }
+}
+
+// One thread per row: X[i,:] = M1[i,:] * (L L^T)^-1 (or * P when info != 0).
+// reference: potrs call src/matrix.c:563 (nrhs = rows).  Row scratch lives in shared memory,
+// laid out [r][thread] so that accesses are conflict-free; L is read as a broadcast.
+__global__ void k_solve_rows(const double * __restrict__ M1, double * __restrict__ X,
+                             unsigned long long I, int R, int ld, const double * __restrict__ L,
+                             const double * __restrict__ P, const int * __restrict__ info) {
+  extern __shared__ double sm[];
+  double * Ls = sm;                         // R*R
+  double * xs = sm + R * R;                 // R * blockDim.x
+  const bool use_p = (*info != 0);
+  const double * src = use_p ? P : L;
+  for (int x = threadIdx.x; x < R * R; x += blockDim.x) Ls[x] = src[x];
+  __syncthreads();
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  const int T = blockDim.x, t = threadIdx.x;
+  const double * row = M1 + i * ld;
+  for (int r = 0; r < R; ++r) xs[r * T + t] = row[r];
+  double * out = X + i * ld;
+  if (!use_p) {
+    for (int p = 0; p < R; ++p) {           // L y = x
+      double s = xs[p * T + t];
+      for (int k = 0; k < p; ++k) s = fma(-Ls[k + p * R], xs[k * T + t], s);
+      xs[p * T + t] = s / Ls[p + p * R];
+    }
+    for (int p = R - 1; p >= 0; --p) {      // L^T z = y
+      double s = xs[p * T + t];
+      for (int k = p + 1; k < R; ++k) s = fma(-Ls[p + k * R], xs[k * T + t], s);
+      s /= Ls[p + p * R];
+      xs[p * T + t] = s;
+      out[p] = s;
+    }
+  } else {
+    for (int j = 0; j < R; ++j) {
+      double s = 0;
+      for (int k = 0; k < R; ++k) s = fma(xs[k * T + t], Ls[j + k * R], s);
+      out[j] = s;
+    }
+  }
+}
+
+// Column sums of squares (two_norm) or column maxima of max(a, 0).
+// reference: p_mat_2norm src/matrix.c:86-144, p_mat_maxnorm :147-199
+__global__ void k_colnorm(const double * __restrict__ A, unsigned long long I, int R, int ld,
+                          int two_norm, double * __restrict__ acc) {
+  const int j = threadIdx.x % 32 + 32 * blockIdx.y;
+  const int ty = threadIdx.x / 32, ny = blockDim.x / 32;
+  double v = 0.0;
+  if (j < R)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * ny + ty; i < I;
+         i += (unsigned long long)gridDim.x * ny) {
+      const double a = A[i * ld + j];
+      v = two_norm ? fma(a, a, v) : fmax(v, a);
+    }
+  __shared__ double red[8][33];
+  red[ty][threadIdx.x % 32] = v;
+  __syncthreads();
+  if (ty == 0 && j < R) {
+    for (int y = 1; y < ny; ++y) v = two_norm ? v + red[y][threadIdx.x] : fmax(v, red[y][threadIdx.x]);
+    if (two_norm) atomicAdd(&acc[j], v);
+    else atomicMax(reinterpret_cast<unsigned long long *>(&acc[j]), (unsigned long long)__double_as_longlong(v));
+  }
+}
+__global__ void k_finish_lambda(double * __restrict__ acc, int R, int two_norm,
+                                double * __restrict__ lambda) {
+  const int j = threadIdx.x + blockIdx.x * blockDim.x;
+  if (j < R) lambda[j] = two_norm ? sqrt(acc[j]) : fmax(acc[j], 1.0);
+}
+__global__ void k_scale_cols(double * __restrict__ A, unsigned long long I, int R, int ld,
+                             const double * __restrict__ lambda) {
+  const unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= I * R) return;
+  const unsigned long long i = x / R;
+  const int j = (int)(x % R);
+  A[i * ld + j] /= lambda[j];
+}
+// inner += sum_i sum_r A[i,r] * M1[i,r] * lambda[r].  reference: p_tt_kruskal_inner src/cpd.c:171-218
+__global__ void k_inner(const double * __restrict__ A, const double * __restrict__ M1,
+                        unsigned long long I, int R, int ld, const double * __restrict__ lambda,
+                        double * __restrict__ inner) {
+  double v = 0.0;
+  for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < I * R;
+       x += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = x / R;
+    const int j = (int)(x % R);
+    v = fma(A[i * ld + j] * M1[i * ld + j], lambda[j], v);
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ double red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(inner, v);
+  }
+}
+
+struct DevTail {
+  int N = 0, R = 0, ld = 0;
+  double * ata = nullptr;     // N x R x R
+  double * chol = nullptr;    // R x R
+  double * pinv = nullptr;    // R x R
+  double * lam_acc = nullptr; // R
+  double * lambda = nullptr;  // R
+  double * inner = nullptr;   // 1
+  int *    info = nullptr;
+  double * h_back = nullptr;  // pinned: N*R*R + R + 1 (+1 info)
+  cudaStream_t s = nullptr;
+
+  bool alloc(int N_, int R_, int ld_, cudaStream_t st) {
+    N = N_; R = R_; ld = ld_; s = st;
+    bool ok = cudaMalloc(&ata, sizeof(double) * N * R * R) == cudaSuccess &&
+              cudaMalloc(&chol, sizeof(double) * R * R) == cudaSuccess &&
+              cudaMalloc(&pinv, sizeof(double) * R * R) == cudaSuccess &&
+              cudaMalloc(&lam_acc, sizeof(double) * R) == cudaSuccess &&
+              cudaMalloc(&lambda, sizeof(double) * R) == cudaSuccess &&
+              cudaMalloc(&inner, sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&info, sizeof(int) * 2) == cudaSuccess &&
+              cudaMallocHost(&h_back, sizeof(double) * ((size_t)N * R * R + R + 2)) == cudaSuccess;
+    if (ok) {
+      cudaFuncSetAttribute(k_form_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * R * R * 8);
+      cudaFuncSetAttribute(k_solve_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (R * R + R * 128) * 8);
+      cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * R * 8);
+    }
+    return ok;
+  }
+  void release() {
+    cudaFree(ata); cudaFree(chol); cudaFree(pinv); cudaFree(lam_acc); cudaFree(lambda);
+    cudaFree(inner); cudaFree(info);
+    if (h_back) cudaFreeHost(h_back);
+  }
+  void gram(const double * A, uint64_t I, int m) {
+    double * G = ata + (size_t)m * R * R;
+    cudaMemsetAsync(G, 0, sizeof(double) * R * R, s);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((I + 31) / 32, 592);
+    k_gram<<<blocks, 256, 32 * R * 8, s>>>(A, I, R, ld, G);
+    g_spb200_launches += 1;
+  }
+  // one mode step after the MTTKRP: d_out (M1) -> d_mat (new factor), lambda, Gram
+  void mode_step(const double * d_out, double * d_mat, uint64_t I, int m, bool two_norm) {
+    k_form_chol<<<1, 256, 2 * R * R * 8, s>>>(ata, N, m, R, chol, pinv, info);
+    k_solve_rows<<<(unsigned)((I + 127) / 128), 128, (R * R + R * 128) * 8, s>>>(
+        d_out, d_mat, I, R, ld, chol, pinv, info);
+    cudaMemsetAsync(lam_acc, 0, sizeof(double) * R, s);
+    dim3 g((unsigned)std::min<uint64_t>((I + 7) / 8, 1184), (R + 31) / 32);
+    k_colnorm<<<g, 256, 0, s>>>(d_mat, I, R, ld, two_norm ? 1 : 0, lam_acc);
+    k_finish_lambda<<<(R + 127) / 128, 128, 0, s>>>(lam_acc, R, two_norm ? 1 : 0, lambda);
+    k_scale_cols<<<(unsigned)((I * R + 255) / 256), 256, 0, s>>>(d_mat, I, R, ld, lambda);
+    g_spb200_launches += 5;
+    gram(d_mat, I, m);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -248,6 +529,10 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
   const int verbosity = (int)options[SPLATT_OPTION_VERBOSITY];
   uint64_t dims[SPB200_MAXN], maxdim = 0;
   for (int m = 0; m < N; ++m) { dims[m] = tensors[0].dims[m]; maxdim = std::max(maxdim, dims[m]); }
+  // Where the dense ALS tail runs.  Default: on the device.
+  // SPLATT_B200_HOST_SOLVE=1 keeps it on the host as the north star words it.
+  const char * hs = getenv("SPLATT_B200_HOST_SOLVE");
+  const bool host_tail = (hs && atoi(hs) != 0) || R > 128;
 
   // device mirror (once) -- reference: splatt_mttkrp_alloc_ws at src/cpd.c:304
   splatt_b200_build_opts bo;
@@ -265,9 +550,10 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
   double * mats[SPB200_MAXN] = {nullptr};
   double * d_mats[SPB200_MAXN] = {nullptr};
   double * d_out = nullptr;
-  double * m1 = nullptr;          // pinned MTTKRP result
+  double * m1 = nullptr;          // pinned MTTKRP result (host tail only)
   double * lambda = static_cast<double *>(malloc(sizeof(double) * R));
   cudaStream_t stream = nullptr;
+  DevTail tail;
   bool ok = lambda != nullptr;
   for (int m = 0; m < N && ok; ++m) {
     mats[m] = static_cast<double *>(malloc(sizeof(double) * dims[m] * R));
@@ -280,6 +566,11 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
     return cudaMemcpy2DAsync(d_mats[m], (size_t)ldm * 8, mats[m], (size_t)R * 8, (size_t)R * 8,
                              dims[m], cudaMemcpyHostToDevice, stream);
   };
+  auto d2h = [&](double * dst, const double * src, uint64_t I) -> cudaError_t {
+    if (ldm == R) return cudaMemcpyAsync(dst, src, I * (size_t)R * 8, cudaMemcpyDeviceToHost, stream);
+    return cudaMemcpy2DAsync(dst, (size_t)R * 8, src, (size_t)ldm * 8, (size_t)R * 8, I,
+                             cudaMemcpyDeviceToHost, stream);
+  };
   ok = ok && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int m = 0; m < N && ok; ++m) {
     ok = cudaMalloc(&d_mats[m], dims[m] * (size_t)ldm * 8) == cudaSuccess &&
@@ -287,25 +578,34 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
          h2d(m) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&d_out, maxdim * (size_t)ldm * 8) == cudaSuccess;
-  ok = ok && cudaMallocHost(&m1, maxdim * (size_t)R * 8) == cudaSuccess;
+  if (host_tail) ok = ok && cudaMallocHost(&m1, maxdim * (size_t)R * 8) == cudaSuccess;
+  else ok = ok && tail.alloc(N, R, ldm, stream);
+
   double fit = 0, oldfit = 0;
-  if (ok) {
-    std::vector<std::vector<double>> ata(N, std::vector<double>((size_t)R * R));
+  const double ttnormsq = csf_frobsq(tensors);
+  const uint64_t niters = (uint64_t)options[SPLATT_OPTION_NITER];
+  std::vector<std::vector<double>> ata(N, std::vector<double>((size_t)R * R));
+  auto report = [&](uint64_t it, double secs) {
+    if (verbosity > SPLATT_VERBOSITY_NONE)
+      printf("  its = %3llu (%0.3fs)  fit = %0.5f  delta = %+0.4e\n", (unsigned long long)it + 1,
+             secs, fit, fit - oldfit);
+  };
+  auto fit_from = [&](double inner) {     // src/cpd.c:237-265
+    const double norm_mats = kruskal_norm(ata, lambda, N, R);
+    double residual = ttnormsq + norm_mats - 2 * inner;
+    if (residual > 0.) residual = std::sqrt(residual);
+    fit = 1 - residual / std::sqrt(ttnormsq);
+  };
+
+  if (ok && host_tail) {
     for (int m = 0; m < N; ++m) gram(mats[m], dims[m], R, ata[m].data());
     std::vector<double> neq((size_t)R * R);
-    const double ttnormsq = csf_frobsq(tensors);
-    const uint64_t niters = (uint64_t)options[SPLATT_OPTION_NITER];
     for (uint64_t it = 0; it < niters && ok; ++it) {
       auto t0 = std::chrono::steady_clock::now();
       for (int m = 0; m < N && ok; ++m) {
         // M1 = X_(m) (khatri-rao of the other factors), on the GPU
         rc = splatt_b200_mttkrp(T, m, R, ldm, d_mats, d_out, stream);
-        cudaError_t e = cudaSuccess;
-        if (ldm == R)
-          e = cudaMemcpyAsync(m1, d_out, dims[m] * (size_t)R * 8, cudaMemcpyDeviceToHost, stream);
-        else
-          e = cudaMemcpy2DAsync(m1, (size_t)R * 8, d_out, (size_t)ldm * 8, (size_t)R * 8, dims[m],
-                                cudaMemcpyDeviceToHost, stream);
+        cudaError_t e = d2h(m1, d_out, dims[m]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (rc != SPLATT_SUCCESS || e != cudaSuccess) { ok = false; break; }
         // A_m = M1 * (hadamard Grams)^-1   (src/cpd.c:337-339, src/matrix.c:529-606)
@@ -323,34 +623,62 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
         ok = h2d(m) == cudaSuccess;                             // keep the device copy current
       }
       if (!ok) break;
-      // fit (src/cpd.c:237-265): uses the last mode's M1
-      const double norm_mats = kruskal_norm(ata, lambda, N, R);
-      const double inner = kruskal_inner(mats[N - 1], m1, dims[N - 1], R, lambda);
-      double residual = ttnormsq + norm_mats - 2 * inner;
-      if (residual > 0.) residual = std::sqrt(residual);
-      fit = 1 - residual / std::sqrt(ttnormsq);
-      const double secs =
-          std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (verbosity > SPLATT_VERBOSITY_NONE)
-        printf("  its = %3llu (%0.3fs)  fit = %0.5f  delta = %+0.4e\n",
-               (unsigned long long)it + 1, secs, fit, fit - oldfit);
+      fit_from(kruskal_inner(mats[N - 1], m1, dims[N - 1], R, lambda));
+      report(it, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
       if (fit == 1. || (it > 0 && std::fabs(fit - oldfit) < options[SPLATT_OPTION_TOLERANCE]))
         break;
       oldfit = fit;
     }
-    // post-process (src/cpd.c:391-411): 2-normalise every factor into lambda
-    if (ok) {
-      std::vector<double> tmp(R);
-      for (int m = 0; m < N; ++m) {
-        normalize_cols(mats[m], dims[m], R, tmp.data(), true);
-        for (int f = 0; f < R; ++f) lambda[f] *= tmp[f];
+  } else if (ok) {
+    // ---- everything on the device; one small read-back per iteration for the fit
+    for (int m = 0; m < N; ++m) tail.gram(d_mats[m], dims[m], m);
+    const size_t nb = (size_t)N * R * R;
+    for (uint64_t it = 0; it < niters && ok; ++it) {
+      auto t0 = std::chrono::steady_clock::now();
+      for (int m = 0; m < N && ok; ++m) {
+        rc = splatt_b200_mttkrp(T, m, R, ldm, d_mats, d_out, stream);
+        if (rc != SPLATT_SUCCESS) { ok = false; break; }
+        tail.mode_step(d_out, d_mats[m], dims[m], m, it == 0);
       }
+      if (!ok) break;
+      cudaMemsetAsync(tail.inner, 0, sizeof(double), stream);
+      k_inner<<<296, 256, 0, stream>>>(d_mats[N - 1], d_out, dims[N - 1], R, ldm, tail.lambda,
+                                       tail.inner);
+      g_spb200_launches += 1;
+      cudaMemcpyAsync(tail.h_back, tail.ata, nb * 8, cudaMemcpyDeviceToHost, stream);
+      cudaMemcpyAsync(tail.h_back + nb, tail.lambda, R * 8, cudaMemcpyDeviceToHost, stream);
+      cudaMemcpyAsync(tail.h_back + nb + R, tail.inner, 8, cudaMemcpyDeviceToHost, stream);
+      cudaMemcpyAsync(tail.h_back + nb + R + 1, tail.info, 4, cudaMemcpyDeviceToHost, stream);
+      if (cudaStreamSynchronize(stream) != cudaSuccess) { ok = false; break; }
+      for (int m = 0; m < N; ++m)
+        memcpy(ata[m].data(), tail.h_back + (size_t)m * R * R, sizeof(double) * R * R);
+      memcpy(lambda, tail.h_back + nb, sizeof(double) * R);
+      int info_last = 0;
+      memcpy(&info_last, tail.h_back + nb + R + 1, sizeof(int));
+      if (info_last)
+        fprintf(stderr, "SPLATT: Gram matrix is not SPD. Used pseudo-inverse.\n");
+      fit_from(tail.h_back[nb + R]);
+      report(it, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      if (fit == 1. || (it > 0 && std::fabs(fit - oldfit) < options[SPLATT_OPTION_TOLERANCE]))
+        break;
+      oldfit = fit;
+    }
+    for (int m = 0; m < N && ok; ++m) ok = d2h(mats[m], d_mats[m], dims[m]) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
+  }
+  // post-process (src/cpd.c:391-411): 2-normalise every factor into lambda
+  if (ok) {
+    std::vector<double> tmp(R);
+    for (int m = 0; m < N; ++m) {
+      normalize_cols(mats[m], dims[m], R, tmp.data(), true);
+      for (int f = 0; f < R; ++f) lambda[f] *= tmp[f];
     }
   }
   if (stream) cudaStreamSynchronize(stream);
   for (int m = 0; m < N; ++m) if (d_mats[m]) cudaFree(d_mats[m]);
   if (d_out) cudaFree(d_out);
   if (m1) cudaFreeHost(m1);
+  if (!host_tail) tail.release();
   if (stream) cudaStreamDestroy(stream);
   splatt_b200_tensor_free(T);
   if (!ok) {

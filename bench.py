@@ -148,8 +148,9 @@ def reference_sweeps(ind_host, vals_host, mats, steps, warmup, nthreads=None):
 
     The reference gets its best thread count: torchrun exports OMP_NUM_THREADS=1 and
     more threads than physical cores hurts it, so unless SPLATT_REF_THREADS pins it we
-    time one sweep at aff, aff/2, aff/4, aff/8 threads (aff = CPUs this process may run
-    on) and keep the fastest."""
+    time one sweep at several thread counts up to aff (= CPUs this process may run on) and
+    keep the fastest (on config 2 the reference privatises its output only below 21 threads,
+    src/mttkrp.c:221-236, which is where it is fastest)."""
     from oracle import ref
     o = ref.default_opts()
     aff = len(os.sched_getaffinity(0))
@@ -171,7 +172,7 @@ def reference_sweeps(ind_host, vals_host, mats, steps, warmup, nthreads=None):
     if nthreads is None and env:
         nthreads = int(env)
     if nthreads is None:
-        cands = sorted({max(1, aff // d) for d in (1, 2, 4, 8)})
+        cands = sorted({t for t in (8, 12, 16, 20, 24, 32, 48, 64, aff // 2, aff) if 1 <= t <= aff})
         trial = {t: float(sweep(t, 1, 1)[0]) for t in cands}
         nthreads = min(trial, key=trial.get)
         log("[reference] sweep seconds by thread count: " +
@@ -231,7 +232,7 @@ def workload_config(n_gpus):
             "seed": SEED}
 
 
-def cpd_iteration_times(S, csf, ind, vals, mats_h):
+def cpd_iteration_times(S, csf, ind, vals, mats_h, ref_threads=None):
     """CPD-ALS seconds per iteration (the metric's second half): splatt_cpd_als of this
     library (MTTKRP + dense tail on the device) vs the reference's, same tensor, rank and
     iteration count; set-up is removed by differencing two iteration counts."""
@@ -252,7 +253,7 @@ def cpd_iteration_times(S, csf, ind, vals, mats_h):
         if ref.available():
             o = ref.default_opts()
             o[1], o[4] = 0.0, 0
-            o[0] = int(os.environ.get("SPLATT_REF_THREADS", "32"))
+            o[0] = ref_threads or int(os.environ.get("SPLATT_REF_THREADS", "16"))
             tt = ref.RefTensor.from_coo([DIM] * NMODES,
                                         [i.cpu().numpy().astype(np.uint64) for i in ind],
                                         vals.cpu().numpy())
@@ -320,14 +321,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # runs through warm-up and the timed region
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         sweep()
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = S.launch_count()
     step_ms, kern_ms = [], [[] for _ in range(NMODES)]
     wall0 = time.time()
@@ -433,7 +433,8 @@ def run_ours(args):
                        "sample": f"failed: {e}"}
         cpd = None
         if world == 1 and not args.no_cpu_baseline:
-            cpd = cpd_iteration_times(S, csf, ind, vals, mats_h)
+            cpd = cpd_iteration_times(S, csf, ind, vals, mats_h,
+                                      cpu.get("cores") if cpu and cpu.get("value") else None)
         line = {"metric": "MTTKRP nnz*R/sec per mode", "value": value, "unit": "nnz*R/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

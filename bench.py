@@ -225,9 +225,9 @@ def workload_config(n_gpus):
                         f"({NNZ_PER_GPU * max(n_gpus,1)} total), rank {RANK} "
                         "(BASELINE.json configs[1] at N=1)",
             "dims": [DIM] * NMODES, "nnz_total": NNZ_PER_GPU * max(n_gpus, 1), "rank": RANK,
-            "step": "one MTTKRP per mode (3 launches + N>1: 3 all-reduces)",
-            "partition": "equal-nnz contiguous shares of every mode's fiber stream; "
-                         "NCCL all-reduce(sum) of the output factor per mode",
+            "step": "one MTTKRP per mode (3 launches; N>1: each followed by the exchange)",
+            "partition": "equal-nnz contiguous shares of every mode's fiber stream; the output "
+                         "factor is summed over ranks once per mode (see exchange)",
             "l2": "flushed between steps (256 MB write, outside the timed events)",
             "seed": SEED}
 
@@ -306,14 +306,31 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     info = [T.mode_info(m, RANK) for m in range(NMODES)]
 
+    # N>1: the exchange is fused into the kernel (multimem.red over NVLink multicast) when
+    # the group supports it; otherwise kernel + NCCL all-reduce.
+    fx = None
+    if world > 1 and not args.nccl_exchange:
+        from splatt_b200 import parallel
+        fx = parallel.FusedExchange(T, RANK)
+        if not fx.available():
+            log(f"[rank {rank}] fused exchange unavailable ({fx.error}); using NCCL all-reduce")
+            fx = None
+    exchange = ("none (single GPU)" if world == 1 else
+                "fused: multimem.red.add.f64 into an NVLink multicast buffer + 1 group barrier"
+                if fx is not None else "NCCL all-reduce(sum) after the kernel")
+
     def sweep(events=None):
         for m in range(NMODES):
             if events is not None:
                 events[m][0].record()
-            T.mttkrp(m, mats, outs[m])
+            if fx is not None:
+                fx.mttkrp(m, mats)        # kernel (reduces into every GPU's buffer) + barrier
+                fx.release(m)             # result consumed: re-zero for the next sweep
+            else:
+                T.mttkrp(m, mats, outs[m])
             if events is not None:
                 events[m][1].record()
-            if world > 1:
+            if world > 1 and fx is None:
                 dist.all_reduce(outs[m])
 
     def barrier():
@@ -412,6 +429,8 @@ def run_ours(args):
                 "launch_ms": k_ms, "traffic": ncu_traffic(),
                 "per_mode_ms": [float(np.mean(k)) for k in kern_ms],
                 "kernel_share_of_step": float(sum(np.mean(k) for k in kern_ms) / ms_per_step),
+                "launch_ms_includes": "memset + kernel" if fx is None else
+                                      "kernel + group barrier + re-zero (fused exchange)",
                 "note": "alg bytes = 16 B/nnz record stream + 4 B/node upper-level ids + "
                         "3 factor-sized matrices (2 read, 1 written); SURVEY 8(d) at stored widths"}
         cpu = None
@@ -439,7 +458,7 @@ def run_ours(args):
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(n_gpus),
+                "config": dict(workload_config(n_gpus), exchange=exchange),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "nnz*R/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -465,6 +484,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="N>1: use kernel + NCCL all-reduce instead of the fused multicast exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -245,7 +245,12 @@ typedef struct
   int32_t shard_count;   /* 0/1 = whole tensor; >1 = keep only this rank's
                             nnz-balanced share of every stream             */
   int32_t verbosity;     /* SPLATT_VERBOSITY_*                             */
-  int32_t reserved[11];
+  int32_t ncolumns_hint; /* rank the tensor will be used with (0 = unknown);
+                            lets the builder size leaf tiles for L1          */
+  int32_t ktile;         /* leaf-tile re-ordering: 0 = automatic (on when
+                            every leaf row would be re-used >= 3x per SM),
+                            -1 = off, > 0 = this many rows per tile          */
+  int32_t reserved[9];
 } splatt_b200_build_opts;
 
 /* Mirror reference CSF(s) (host memory) into HBM.  `csf_alloc` says how many
@@ -325,6 +330,24 @@ int splatt_b200_mttkrp(
     int ldm,
     double const * const * d_mats,
     double * d_out,
+    void * stream);
+
+/* Fused MTTKRP + exchange for sharded tensors on one NVSwitch domain.  `mc_out` is
+ * an NVLink MULTICAST address (CUDA multicast object / torch symmetric memory
+ * `multicast_ptr`) bound to one dims[mode] x ldm buffer on every GPU of the
+ * group.  The kernel adds every finished output row into ALL the buffers with
+ * `multimem.red.add.f64` as it goes, so the per-mode all-reduce of the north star
+ * happens inside the MTTKRP kernel instead of after it.  Contract: every rank
+ * zeroes its own buffer and the group synchronises BEFORE the call; after the
+ * call the group synchronises once more and every buffer holds the full sum.
+ * Requires the ALLROOT layout (root kernels).  Not zeroed, not synchronised here. */
+int splatt_b200_mttkrp_multicast(
+    splatt_b200_tensor const * t,
+    int mode,
+    int ncolumns,
+    int ldm,
+    double const * const * d_mats,
+    double * mc_out,
     void * stream);
 
 /* Number of kernels the engine has launched in this process (bench.py's

@@ -33,7 +33,9 @@ else:
     ind = [torch.randint(0, dim, (nnz,), device="cuda", dtype=torch.int32, generator=g) for _ in range(N)]
 vals = torch.rand(nnz, device="cuda", dtype=torch.float64, generator=g)
 t0 = time.time()
-T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=1, verbosity=3)
+import os
+T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=1, verbosity=3,
+                      ncolumns_hint=R, ktile=int(os.environ.get("KTILE", "-1")))
 torch.cuda.synchronize()
 print(f"build {time.time()-t0:.2f}s  device MB {T.device_bytes/1e6:.0f}")
 mats = [torch.rand(d, R, device="cuda", dtype=torch.float64) * 6 - 3 for d in dims]

@@ -78,7 +78,8 @@ class Matrix(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("layout", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
                 ("shard_count", C.c_int32), ("verbosity", C.c_int32),
-                ("reserved", C.c_int32 * 11)]
+                ("ncolumns_hint", C.c_int32), ("ktile", C.c_int32),
+                ("reserved", C.c_int32 * 9)]
 
 
 LIB_PATH = Path(__file__).resolve().parent / "libsplatt_b200.so"
@@ -90,7 +91,7 @@ EXPORTS = [
     "splatt_b200_tensor_from_csf", "splatt_b200_tensor_from_coo", "splatt_b200_tensor_free",
     "splatt_b200_tensor_info", "splatt_b200_mode_info", "splatt_b200_csf_alloc",
     "splatt_b200_csf_free", "splatt_b200_mttkrp", "splatt_b200_launch_count",
-    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range",
+    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast",
 ]
 
 _lib = None
@@ -151,6 +152,9 @@ def load() -> C.CDLL:
     lib.splatt_b200_mttkrp.restype = C.c_int
     lib.splatt_b200_mttkrp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp, val_p,
                                        C.c_void_p]
+    lib.splatt_b200_mttkrp_multicast.restype = C.c_int
+    lib.splatt_b200_mttkrp_multicast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp, val_p,
+                                                 C.c_void_p]
     lib.splatt_b200_launch_count.restype = C.c_uint64
     lib.splatt_b200_launch_count.argtypes = []
     lib.splatt_b200_version.restype = C.c_char_p

@@ -219,8 +219,10 @@ class Tensor:
         self.device_bytes = int(byt.value)
 
     @staticmethod
-    def _bopts(layout, device, shard_rank, shard_count, verbosity):
+    def _bopts(layout, device, shard_rank, shard_count, verbosity, ncolumns_hint=0, ktile=0):
         bo = A.BuildOpts()
+        bo.ncolumns_hint = ncolumns_hint
+        bo.ktile = ktile
         bo.layout = layout
         bo.device = device
         bo.shard_rank = shard_rank
@@ -231,8 +233,10 @@ class Tensor:
     @classmethod
     def from_coo(cls, dims, ind, vals, *, csf_alloc: int = A.CSF_TWOMODE,
                  layout: int = A.LAYOUT_ALLROOT, device: int = -1, shard_rank: int = 0,
-                 shard_count: int = 1, verbosity: int = 0) -> "Tensor":
-        """ind/vals: numpy (host) arrays, or torch CUDA tensors (int32/uint32 + float64)."""
+                 shard_count: int = 1, verbosity: int = 0, ncolumns_hint: int = 0,
+                 ktile: int = 0) -> "Tensor":
+        """ind/vals: numpy (host) arrays, or torch CUDA tensors (int32/uint32 + float64).
+        ncolumns_hint: the rank the tensor will be multiplied at (enables leaf tiling)."""
         lib = A.load()
         on_device = 0
         try:
@@ -241,7 +245,7 @@ class Tensor:
                 on_device = 1
         except ImportError:
             pass
-        bo = cls._bopts(layout, device, shard_rank, shard_count, verbosity)
+        bo = cls._bopts(layout, device, shard_rank, shard_count, verbosity, ncolumns_hint, ktile)
         out = C.c_void_p()
         if on_device:
             dims_a = np.ascontiguousarray(dims, dtype=np.uint64)
@@ -264,9 +268,10 @@ class Tensor:
 
     @classmethod
     def from_csf(cls, csf_ptr, csf_alloc: int, *, layout: int = A.LAYOUT_ALLROOT, device: int = -1,
-                 shard_rank: int = 0, shard_count: int = 1, verbosity: int = 0) -> "Tensor":
+                 shard_rank: int = 0, shard_count: int = 1, verbosity: int = 0,
+                 ncolumns_hint: int = 0, ktile: int = 0) -> "Tensor":
         lib = A.load()
-        bo = cls._bopts(layout, device, shard_rank, shard_count, verbosity)
+        bo = cls._bopts(layout, device, shard_rank, shard_count, verbosity, ncolumns_hint, ktile)
         out = C.c_void_p()
         rc = lib.splatt_b200_tensor_from_csf(csf_ptr, csf_alloc, C.byref(bo), C.byref(out))
         _check(rc, "splatt_b200_tensor_from_csf")

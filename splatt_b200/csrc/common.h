@@ -49,12 +49,20 @@ struct FiberStream {
   int      perm[SPB200_MAXN] = {0};       // level -> mode
   uint64_t nrec = 0;                       // records held (local)
   uint64_t nrec_total = 0;                 // records in the whole tensor
-  uint64_t nnodes[SPB200_MAXN] = {0};     // nodes per level (whole tensor)
+  uint64_t nnodes[SPB200_MAXN] = {0};     // nodes per level (of the records held)
   SpRec *    rec = nullptr;
-  uint32_t * up[SPB200_MAXN] = {nullptr}; // levels 0..N-3 (whole arrays)
+  uint32_t * up[SPB200_MAXN] = {nullptr}; // levels 0..N-3 (of the records held)
   uint32_t * desc = nullptr;               // local chunks x (N-2)
   uint64_t nchunks = 0;                    // local chunks
   size_t   bytes = 0;                      // HBM held
+  uint32_t ktile_rows = 0;                 // >0: leaf-tile re-ordered (rows per tile)
+  uint32_t kranges = 0;                    //     ... inside this many chunk-aligned ranges
+};
+
+// Leaf-tile re-ordering request for spb200_build_stream (tile_rows == 0: off).
+struct StreamTiling {
+  uint32_t tile_rows = 0;
+  uint32_t nranges = 0;
 };
 
 enum { SPB200_KIND_ROOT = 0, SPB200_KIND_INTL = 1, SPB200_KIND_LEAF = 2 };
@@ -89,6 +97,8 @@ struct MttkrpArgs {
   int              ncols;     // active columns in this launch (even, <= 2*L)
   int              col0;      // first column of this launch
   int              outdepth;  // level of the output mode
+  int              ktiled;    // stream is leaf-tile ordered: keep non-leaf gathers out of L1
+  int              multicast; // `out` is an NVLink multicast address: reduce with multimem.red
 };
 
 #define SPB200_CUDA_OK(call)                                                   \
@@ -112,7 +122,7 @@ int spb200_build_stream(int nmodes, const uint64_t * dims, uint64_t nnz,
                         const uint32_t * const * d_ind, const double * d_vals,
                         const int * perm, bool presorted,
                         int shard_rank, int shard_count,
-                        FiberStream * out);
+                        const StreamTiling & tiling, FiberStream * out);
 void spb200_free_stream(FiberStream * s);
 
 // Host CSF arrays from device COO (for splatt_b200_csf_alloc).
@@ -124,5 +134,5 @@ int spb200_build_host_csf(int nmodes, const uint64_t * dims, uint64_t nnz,
 int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
                          int ncolumns, int ldm,
                          const double * const * d_mats_by_mode, double * d_out,
-                         uint64_t out_rows, cudaStream_t stream);
+                         uint64_t out_rows, cudaStream_t stream, bool multicast_out = false);
 extern unsigned long long g_spb200_launches;

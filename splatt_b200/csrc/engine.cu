@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------
 // Level orders.  Semantics of csf_find_mode_order (reference: src/csf.c:694-726):
@@ -170,10 +171,48 @@ int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
   T->shard_count = bo.shard_count > 1 ? bo.shard_count : 1;
   SPB200_CUDA_OK(cudaGetDevice(&T->device));
   T->streams.resize(stream_perms.size());
+  int num_sms = 148;
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, T->device);
   for (size_t i = 0; i < stream_perms.size(); ++i) {
+    // Leaf-tile re-ordering policy.  Worth it only when a leaf row is re-used several
+    // times by the nonzeros one SM processes (otherwise every row is fetched once
+    // anyway) and the leaf factor does not already fit in L1.
+    StreamTiling tiling;
+    const bool is_root_stream = true;   // decided per plan below; tiling is only used by root kernels
+    (void)is_root_stream;
+    // Measured on config 2: without a CTA-wide barrier per tile the lane
+    // groups of an SM drift apart by several tiles, the L1 working set never shrinks and
+    // the extra segment boundaries only cost REDs -- so the automatic mode stays off and the
+    // layout is opt-in (ktile > 0, or SPLATT_B200_KTILE_AUTO=1 to apply the heuristic).
+    const char * auto_env = getenv("SPLATT_B200_KTILE_AUTO");
+    const bool allow_auto = auto_env && atoi(auto_env) != 0;
+    if (bo.ktile > 0 || (bo.ktile == 0 && allow_auto && bo.ncolumns_hint > 0)) {
+      const uint64_t leaf_dim = dims[stream_perms[i].perm[N - 1]];
+      uint64_t c0, c1;
+      spb200_shard_chunks(dc.nnz, T->shard_rank, T->shard_count, &c0, &c1);
+      const uint64_t local = std::min<uint64_t>(c1 * SPB200_CHUNK, dc.nnz) - c0 * SPB200_CHUNK;
+      uint32_t rows = 0;
+      if (bo.ktile > 0) rows = (uint32_t)bo.ktile;
+      else {
+        const uint64_t rowbytes = (uint64_t)(bo.ncolumns_hint + (bo.ncolumns_hint & 1)) * 8;
+        const char * e = getenv("SPLATT_B200_L1_TILE_KB");
+        const uint64_t budget = (e ? (uint64_t)atoi(e) : 64) * 1024;
+        rows = (uint32_t)std::max<uint64_t>(budget / std::max<uint64_t>(rowbytes, 8), 16);
+        const double reuse = (double)local / num_sms / (double)std::max<uint64_t>(leaf_dim, 1);
+        if (reuse < 3.0 || leaf_dim <= rows) rows = 0;
+      }
+      if (rows > 0) {
+        tiling.tile_rows = rows;
+        tiling.nranges = (uint32_t)num_sms * 48u;
+        const uint64_t ntiles = (leaf_dim + rows - 1) / rows;
+        if ((uint64_t)tiling.nranges * ntiles >= 0xffffffffull ||
+            (bo.ktile == 0 && local < (uint64_t)tiling.nranges * 256))
+          tiling = StreamTiling();
+      }
+    }
     int rc = spb200_build_stream(N, dims, dc.nnz, dc.ind, dc.vals, stream_perms[i].perm,
                                  stream_perms[i].presorted, T->shard_rank, T->shard_count,
-                                 &T->streams[i]);
+                                 tiling, &T->streams[i]);
     if (rc != SPLATT_SUCCESS) { splatt_b200_tensor_free(T); return rc; }
     if (bo.verbosity >= SPLATT_VERBOSITY_MAX) {
       const FiberStream & s = T->streams[i];
@@ -182,7 +221,9 @@ int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
       printf("] nodes [");
       for (int l = 0; l < N; ++l)
         printf("%llu%s", (unsigned long long)s.nnodes[l], l + 1 < N ? " " : "");
-      printf("] local records %llu, %.1f MB\n", (unsigned long long)s.nrec, s.bytes / 1e6);
+      printf("] local records %llu, %.1f MB", (unsigned long long)s.nrec, s.bytes / 1e6);
+      if (s.ktile_rows) printf(", leaf tiles of %u rows in %u ranges", s.ktile_rows, s.kranges);
+      printf("\n");
     }
   }
   for (int m = 0; m < N; ++m) T->plan[m] = plan[m];
@@ -381,9 +422,8 @@ int splatt_b200_mode_info(splatt_b200_tensor const * t, int mode, int ncolumns, 
     // every array touched once, at the widths stored on device
     // (values 8 B, indices 4 B; fptr replaced by per-record flags that ride
     // in the index words, so the fptr term is the 4 B/nnz parent word).
-    const double frac = t->nnz_total ? (double)s.nrec / (double)t->nnz_total : 0.0;
     uint64_t b = s.nrec * sizeof(SpRec);
-    for (int l = 0; l <= N - 3; ++l) b += (uint64_t)(s.nnodes[l] * frac) * 4;
+    for (int l = 0; l <= N - 3; ++l) b += s.nnodes[l] * 4;   // node counts are this shard's
     for (int m = 0; m < N; ++m) b += t->dims[m] * (uint64_t)ncolumns * 8;   // N-1 reads + 1 write
     *alg_bytes = b;
   }
@@ -399,6 +439,17 @@ int splatt_b200_mttkrp(splatt_b200_tensor const * t, int mode, int ncolumns, int
   const ModePlan & p = t->plan[mode];
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
                               d_out, t->dims[mode], static_cast<cudaStream_t>(stream));
+}
+
+int splatt_b200_mttkrp_multicast(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
+                                 double const * const * d_mats, double * mc_out, void * stream) {
+  if (!t || !d_mats || !mc_out || mode < 0 || mode >= t->nmodes) {
+    fprintf(stderr, "SPLATT: splatt_b200_mttkrp_multicast: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const ModePlan & p = t->plan[mode];
+  return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
+                              mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true);
 }
 
 int splatt_b200_csf_alloc(int nmodes, uint64_t const * dims, uint64_t nnz,

@@ -10,9 +10,9 @@ int spb200_root_batch();
 
 namespace spb200 {
 
-template <int N, int L, int KIND, int BATCH>
+template <int N, int L, int KIND, int BATCH, bool KT = false, bool MC = false>
 static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
-  auto kern = mttkrp_stream_kernel<N, L, KIND, BATCH>;
+  auto kern = mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC>;
   static int occ = 0;   // per-variant, set once
   if (occ == 0) {
     SPB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -37,7 +37,10 @@ template <int N, int L>
 static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
   switch (kind) {
     case SPB200_KIND_ROOT:
+      if (args.multicast) return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, true>(args, num_sms, stream);
       if (spb200_root_batch() >= 8) return launch_variant<N, L, SPB200_KIND_ROOT, 8>(args, num_sms, stream);
+      if (spb200_root_batch() == 2) return launch_variant<N, L, SPB200_KIND_ROOT, 2>(args, num_sms, stream);
+      if (args.ktiled) return launch_variant<N, L, SPB200_KIND_ROOT, 4, true>(args, num_sms, stream);
       return launch_variant<N, L, SPB200_KIND_ROOT, 4>(args, num_sms, stream);
     case SPB200_KIND_INTL: return launch_variant<N, L, SPB200_KIND_INTL, 4>(args, num_sms, stream);
     default:               return launch_variant<N, L, SPB200_KIND_LEAF, 4>(args, num_sms, stream);

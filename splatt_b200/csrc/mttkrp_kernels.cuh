@@ -82,11 +82,30 @@ __device__ __forceinline__ double2 ld_row(const char * __restrict__ base, uint32
                                           uint32_t pitch) {
   return __ldg(reinterpret_cast<const double2 *>(base + static_cast<uint64_t>(idx) * pitch));
 }
+// Same gather, but the line is not allocated in L1 (parent rows of a leaf-tiled stream
+// are touched once per SM: keeping them out leaves L1 to the leaf tile).
+__device__ __forceinline__ double2 ld_row_na(const char * __restrict__ base, uint32_t idx,
+                                             uint32_t pitch) {
+  double2 r;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(base + static_cast<uint64_t>(idx) * pitch));
+  return r;
+}
 __device__ __forceinline__ void red_row(char * __restrict__ base, uint32_t idx, uint32_t pitch,
                                         double2 x) {
   double * p = reinterpret_cast<double *>(base + static_cast<uint64_t>(idx) * pitch);
   atomicAdd(p, x.x);      // result unused -> RED.E.ADD.F64
   atomicAdd(p + 1, x.y);
+}
+// The same reduction through an NVLink MULTICAST address: one instruction adds the value
+// into the row of every GPU of the group (NVSwitch fans it out).  Used by the fused
+// MTTKRP + exchange path: the finished output rows never take a separate collective.
+__device__ __forceinline__ void red_row_mc(char * __restrict__ base, uint32_t idx, uint32_t pitch,
+                                           double2 x) {
+  double * p = reinterpret_cast<double *>(base + static_cast<uint64_t>(idx) * pitch);
+  asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(x.x) : "memory");
+  asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(x.y) : "memory");
 }
 __device__ __forceinline__ double2 fma2(double s, double2 a, double2 c) {
   return make_double2(fma(s, a.x, c.x), fma(s, a.y, c.y));
@@ -101,7 +120,7 @@ __device__ __forceinline__ double2 mul2(double2 a, double2 b) {
 // One record of the root traversal (levels above the leaf fold upwards; the
 // root row leaves the SM with a RED).  `b`/`r` are the gathered leaf / parent
 // rows; for N >= 4 `r2` is the gathered level-(N-3) row (valid when c >= 2).
-template <int N>
+template <int N, bool MC>
 __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q, const double2 b,
                                             const double2 r, const double2 r2,
                                             double2 (&acc)[N - 1], uint32_t (&pos)[N - 2],
@@ -132,14 +151,15 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
       if (c >= uint32_t(N - 1)) {
         const uint32_t row = __ldg(&a.up[0][pos[0]]);
         ++pos[0];
-        red_row(obase, row, pitch, acc[0]);
+        if constexpr (MC) red_row_mc(obase, row, pitch, acc[0]);
+        else red_row(obase, row, pitch, acc[0]);
         acc[0] = zero2;
       }
     }
   }
 }
 
-template <int N, int L, int KIND, int BATCH>
+template <int N, int L, int KIND, int BATCH, bool KT, bool MC>
 __global__ void __launch_bounds__(kThreads, ((BATCH >= 8 || N >= 4) ? 2 : 3))
 mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
@@ -248,7 +268,9 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
           for (int u = 0; u < BATCH; ++u) b[u] = ld_row(mbase[N - 1], q[u].z, pitch);
 #pragma unroll
           for (int u = 0; u < BATCH; ++u)
-            if (q[u].w >> SPB200_IDX_BITS) r[u] = ld_row(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch);
+            if (q[u].w >> SPB200_IDX_BITS)
+              r[u] = KT ? ld_row_na(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch)
+                        : ld_row(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch);
           uint32_t p2 = 0;
           if constexpr (N >= 4) {
             // level N-3 closes are frequent on deep trees: their ids are the next
@@ -286,7 +308,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
           } else {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
-              root_record<N>(a, q[u], b[u], r[u], r2[u], acc, pos, mbase, obase, pitch);
+              root_record<N, MC>(a, q[u], b[u], r[u], r2[u], acc, pos, mbase, obase, pitch);
           }
         }
         for (; n0 < cnt; ++n0) {   // tail of the range's last stage
@@ -298,7 +320,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
             if ((q.w >> SPB200_IDX_BITS) >= 2u)
               r2 = ld_row(mbase[N - 3], __ldg(&a.up[N - 3][pos[N - 3]]), pitch);
           }
-          root_record<N>(a, q, b, r, r2, acc, pos, mbase, obase, pitch);
+          root_record<N, MC>(a, q, b, r, r2, acc, pos, mbase, obase, pitch);
         }
       } else if constexpr (KIND == SPB200_KIND_INTL) {
 #pragma unroll 2

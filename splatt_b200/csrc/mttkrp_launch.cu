@@ -9,7 +9,8 @@ int spb200_root_batch() {
   static int v = -1;
   if (v < 0) {
     const char * e = getenv("SPLATT_B200_BATCH");
-    v = (e && atoi(e) >= 8) ? 8 : 4;
+    v = e ? atoi(e) : 0;   // 0 = per-kernel default (4)
+    if (v != 2 && v != 8) v = 4;
   }
   return v;
 }
@@ -38,7 +39,7 @@ static int num_sms_of_current_device() {
 
 int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncolumns, int ldm,
                          const double * const * d_mats_by_mode, double * d_out,
-                         uint64_t out_rows, cudaStream_t stream) {
+                         uint64_t out_rows, cudaStream_t stream, bool multicast_out) {
   const int N = s.nmodes;
   if (N < 3 || N > SPB200_MAXN) {
     fprintf(stderr, "SPLATT: MTTKRP supports 3..%d modes (got %d)\n", SPB200_MAXN, N);
@@ -49,7 +50,15 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
             ncolumns, ldm);
     return SPLATT_ERROR_BADINPUT;
   }
-  SPB200_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * out_rows * ldm, stream));
+  if (multicast_out) {
+    // the caller zeroed every GPU's buffer and synchronised the group beforehand
+    if (kind != SPB200_KIND_ROOT) {
+      fprintf(stderr, "SPLATT: multicast output needs a root-oriented stream (ALLROOT layout)\n");
+      return SPLATT_ERROR_BADINPUT;
+    }
+  } else {
+    SPB200_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * out_rows * ldm, stream));
+  }
   if (s.nrec == 0) return SPLATT_SUCCESS;
 
   MttkrpArgs a;
@@ -62,6 +71,8 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   a.nchunks  = static_cast<unsigned int>(s.nchunks);
   a.ldm      = ldm;
   a.outdepth = outdepth;
+  a.ktiled   = s.ktile_rows ? 1 : 0;
+  a.multicast = multicast_out ? 1 : 0;
 
   const int rpad    = ncolumns + (ncolumns & 1);
   const int num_sms = num_sms_of_current_device();

@@ -140,10 +140,9 @@ inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 struct SortedCoo {
   int N = 0;
   uint64_t nnz = 0;
-  DevBuf order;                 // uint32[nnz] (empty if presorted)
+  DevBuf order;                 // uint32[nnz]: source nonzero of every record
   DevBuf sidx[SPB200_MAXN];     // uint32[nnz] per level
   DevBuf dl;                    // uint8[nnz]
-  const uint32_t * order_ptr() { return order.p ? order.as<uint32_t>() : nullptr; }
 };
 
 #define CK(call)                                                                        \
@@ -157,10 +156,11 @@ struct SortedCoo {
     }                                                                                   \
   } while (0)
 
-int sort_coo(int N, const uint64_t * dims, uint64_t nnz, const uint32_t * const * d_ind,
-             const int * perm, bool presorted, SortedCoo * sc) {
-  sc->N = N;
-  sc->nnz = nnz;
+// Sort the whole tensor lexicographically in level order: leaves sc->order
+// (empty when presorted).  LSD radix passes; as many trailing levels as fit are
+// packed into one 64-bit key.
+int sort_order(int N, const uint64_t * dims, uint64_t nnz, const uint32_t * const * d_ind,
+               const int * perm, bool presorted, DevBuf * order) {
   if (nnz >= 0xffffffffull) {
     fprintf(stderr, "SPLATT: tensors with >= 2^32 nonzeros per device are not supported\n");
     return SPLATT_ERROR_BADINPUT;
@@ -173,50 +173,123 @@ int sort_coo(int N, const uint64_t * dims, uint64_t nnz, const uint32_t * const 
       return SPLATT_ERROR_BADINPUT;
     }
   }
-  if (!presorted && nnz > 0) {
-    CK(sc->order.alloc(nnz * 4));
-    DevBuf order_alt, keys, keys_alt, tmp;
-    CK(order_alt.alloc(nnz * 4));
-    CK(keys.alloc(nnz * 8));
-    CK(keys_alt.alloc(nnz * 8));
-    k_iota<<<nblk(nnz), 256>>>(sc->order.as<uint32_t>(), nnz);
-    // LSD passes: pack as many trailing levels as fit into one 64-bit key.
-    int l = N - 1;
+  if (presorted || nnz == 0) return SPLATT_SUCCESS;
+  CK(order->alloc(nnz * 4));
+  DevBuf order_alt, keys, keys_alt, tmp;
+  CK(order_alt.alloc(nnz * 4));
+  CK(keys.alloc(nnz * 8));
+  CK(keys_alt.alloc(nnz * 8));
+  k_iota<<<nblk(nnz), 256>>>(order->as<uint32_t>(), nnz);
+  int l = N - 1;
+  while (l >= 0) {
+    KeySpec ks; ks.n = 0;
+    int used = 0;
     while (l >= 0) {
-      KeySpec ks; ks.n = 0;
-      int used = 0;
-      while (l >= 0) {
-        const int b = bits_for(dims[perm[l]]);
-        if (used + b > 64) break;
-        ks.src[ks.n] = d_ind[perm[l]];
-        ks.shift[ks.n] = used;
-        ++ks.n;
-        used += b;
-        --l;
-      }
-      k_make_keys<<<nblk(nnz), 256>>>(ks, sc->order.as<uint32_t>(), nnz, keys.as<uint64_t>());
-      cub::DoubleBuffer<uint64_t> kb(keys.as<uint64_t>(), keys_alt.as<uint64_t>());
-      cub::DoubleBuffer<uint32_t> vb(sc->order.as<uint32_t>(), order_alt.as<uint32_t>());
-      size_t tb = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int64_t)nnz, 0, used));
-      if (tb > tmp.bytes) CK(tmp.alloc(tb));
-      CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int64_t)nnz, 0, used));
-      if (vb.Current() != sc->order.as<uint32_t>()) std::swap(sc->order.p, order_alt.p);
-      if (kb.Current() != keys.as<uint64_t>()) std::swap(keys.p, keys_alt.p);
+      const int b = bits_for(dims[perm[l]]);
+      if (used + b > 64) break;
+      ks.src[ks.n] = d_ind[perm[l]];
+      ks.shift[ks.n] = used;
+      ++ks.n;
+      used += b;
+      --l;
     }
-    CK(cudaGetLastError());
+    k_make_keys<<<nblk(nnz), 256>>>(ks, order->as<uint32_t>(), nnz, keys.as<uint64_t>());
+    cub::DoubleBuffer<uint64_t> kb(keys.as<uint64_t>(), keys_alt.as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> vb(order->as<uint32_t>(), order_alt.as<uint32_t>());
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int64_t)nnz, 0, used));
+    if (tb > tmp.bytes) CK(tmp.alloc(tb));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int64_t)nnz, 0, used));
+    if (vb.Current() != order->as<uint32_t>()) std::swap(order->p, order_alt.p);
+    if (kb.Current() != keys.as<uint64_t>()) std::swap(keys.p, keys_alt.p);
+  }
+  CK(cudaGetLastError());
+  return SPLATT_SUCCESS;
+}
+
+// Leaf-tile re-ordering ("k-tiling").  The local records are cut into `nranges`
+// chunk-aligned ranges (the same cut the kernel makes when it hands ranges to
+// lane groups); inside every range the records are regrouped by
+// leaf-index tile = leaf / tile_rows, keeping CSF order inside a (range, tile)
+// segment.  All groups of an SM then sweep the leaf factor tile by tile at the
+// same pace, so the rows of the current tile stay L1-resident and are re-used
+// instead of being fetched from L2 once per nonzero.  seg[n] = segment id of
+// local record n (segment changes force a node break at every level).
+__global__ void k_tile_keys(const uint32_t * __restrict__ leaf_src,
+                            const uint32_t * __restrict__ lorder, uint64_t n0, uint64_t nrec,
+                            uint64_t nchunks, uint32_t nranges, uint32_t tile_rows,
+                            uint32_t ntiles, uint32_t * __restrict__ keys,
+                            uint32_t * __restrict__ pos) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nrec) return;
+  const uint64_t c = i / SPB200_CHUNK;
+  uint64_t r = ((c + 1) * nranges - 1) / nchunks;        // largest r with r*nchunks/nranges <= c
+  if (r >= nranges) r = nranges - 1;
+  const uint32_t src = lorder ? lorder[i] : (uint32_t)(n0 + i);
+  keys[i] = (uint32_t)r * ntiles + leaf_src[src] / tile_rows;
+  pos[i]  = src;
+}
+
+int tile_local_order(const uint32_t * leaf_src, const uint32_t * lorder, uint64_t n0,
+                     uint64_t nrec, uint32_t nranges, uint32_t tile_rows, uint32_t ntiles,
+                     DevBuf * new_order, DevBuf * seg) {
+  const uint64_t nchunks = (nrec + SPB200_CHUNK - 1) / SPB200_CHUNK;
+  DevBuf keys_alt, pos_alt, tmp;
+  CK(seg->alloc(nrec * 4));
+  CK(new_order->alloc(nrec * 4));
+  CK(keys_alt.alloc(nrec * 4));
+  CK(pos_alt.alloc(nrec * 4));
+  k_tile_keys<<<nblk(nrec), 256>>>(leaf_src, lorder, n0, nrec, nchunks, nranges, tile_rows,
+                                   ntiles, seg->as<uint32_t>(), new_order->as<uint32_t>());
+  cub::DoubleBuffer<uint32_t> kb(seg->as<uint32_t>(), keys_alt.as<uint32_t>());
+  cub::DoubleBuffer<uint32_t> vb(new_order->as<uint32_t>(), pos_alt.as<uint32_t>());
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < (uint64_t)nranges * ntiles) ++bits;
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int64_t)nrec, 0, bits));
+  CK(tmp.alloc(tb));
+  CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int64_t)nrec, 0, bits));   // stable
+  if (vb.Current() != new_order->as<uint32_t>()) std::swap(new_order->p, pos_alt.p);
+  if (kb.Current() != seg->as<uint32_t>()) std::swap(seg->p, keys_alt.p);
+  CK(cudaGetLastError());
+  return SPLATT_SUCCESS;
+}
+
+__global__ void k_offset_iota(uint32_t * o, uint64_t n0, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) o[i] = (uint32_t)(n0 + i);
+}
+
+__global__ void k_seg_breaks(const uint32_t * __restrict__ seg, uint64_t n,
+                             uint8_t * __restrict__ dl) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > 0 && i < n && seg[i] != seg[i - 1]) dl[i] = 0;
+}
+
+// Gather the per-level indices of `count` records taken in the order `ord`
+// (ord[i] = source nonzero) and compute their first-differing levels.
+int gather_levels(int N, const uint32_t * const * d_ind, const int * perm, const uint32_t * ord,
+                  uint64_t n0, uint64_t count, const uint32_t * seg, SortedCoo * sc) {
+  sc->N = N;
+  sc->nnz = count;
+  // materialise the order so later stages can index values with it
+  CK(sc->order.alloc(count * 4));
+  if (count) {
+    if (ord) CK(cudaMemcpy(sc->order.p, ord, count * 4, cudaMemcpyDeviceToDevice));
+    else k_offset_iota<<<nblk(count), 256>>>(sc->order.as<uint32_t>(), n0, count);
   }
   for (int lv = 0; lv < N; ++lv) {
-    CK(sc->sidx[lv].alloc(nnz * 4));
-    if (nnz)
-      k_gather_u32<<<nblk(nnz), 256>>>(d_ind[perm[lv]], sc->order_ptr(), nnz,
-                                       sc->sidx[lv].as<uint32_t>());
+    CK(sc->sidx[lv].alloc(count * 4));
+    if (count)
+      k_gather_u32<<<nblk(count), 256>>>(d_ind[perm[lv]], sc->order.as<uint32_t>(), count,
+                                         sc->sidx[lv].as<uint32_t>());
   }
-  CK(sc->dl.alloc(nnz));
-  if (nnz) {
+  CK(sc->dl.alloc(count));
+  if (count) {
     LevelPtrs lp;
     for (int lv = 0; lv < SPB200_MAXN; ++lv) lp.s[lv] = lv < N ? sc->sidx[lv].as<uint32_t>() : nullptr;
-    k_first_diff<<<nblk(nnz), 256>>>(lp, N, nnz, sc->dl.as<uint8_t>());
+    k_first_diff<<<nblk(count), 256>>>(lp, N, count, sc->dl.as<uint8_t>());
+    if (seg) k_seg_breaks<<<nblk(count), 256>>>(seg, count, sc->dl.as<uint8_t>());
   }
   CK(cudaGetLastError());
   return SPLATT_SUCCESS;
@@ -254,27 +327,52 @@ void spb200_free_stream(FiberStream * s) {
 
 int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
                         const uint32_t * const * d_ind, const double * d_vals, const int * perm,
-                        bool presorted, int shard_rank, int shard_count, FiberStream * out) {
+                        bool presorted, int shard_rank, int shard_count,
+                        const StreamTiling & tiling, FiberStream * out) {
   *out = FiberStream();
   out->nmodes = N;
   for (int l = 0; l < N; ++l) out->perm[l] = perm[l];
   out->nrec_total = nnz;
 
-  SortedCoo sc;
-  int rc = sort_coo(N, dims, nnz, d_ind, perm, presorted, &sc);
+  // 1. whole-tensor CSF order
+  DevBuf order;
+  int rc = sort_order(N, dims, nnz, d_ind, perm, presorted, &order);
   if (rc != SPLATT_SUCCESS) return rc;
 
-  // shard = contiguous, equal-count range of chunks
+  // 2. this shard = a contiguous, equal-count range of 64-record chunks
   uint64_t c0 = 0, c1 = 0;
   spb200_shard_chunks(nnz, shard_rank, shard_count, &c0, &c1);
   const uint64_t r0 = c0 * SPB200_CHUNK;
   const uint64_t r1 = std::min<uint64_t>(c1 * SPB200_CHUNK, nnz);
   out->nchunks = c1 - c0;
   out->nrec = (r1 > r0) ? (r1 - r0) : 0;
+  const uint64_t nrec = out->nrec;
+  const uint32_t * lorder = order.p ? order.as<uint32_t>() + r0 : nullptr;
+
+  // 3. optional leaf-tile re-ordering inside kernel ranges
+  DevBuf tiled_order, seg;
+  const bool tiled = tiling.tile_rows > 0 && tiling.nranges > 0 && nrec > 0 &&
+                     dims[perm[N - 1]] > tiling.tile_rows;
+  if (tiled) {
+    const uint32_t ntiles = (uint32_t)((dims[perm[N - 1]] + tiling.tile_rows - 1) / tiling.tile_rows);
+    rc = tile_local_order(d_ind[perm[N - 1]], lorder, r0, nrec, tiling.nranges, tiling.tile_rows,
+                          ntiles, &tiled_order, &seg);
+    if (rc != SPLATT_SUCCESS) return rc;
+    lorder = tiled_order.as<uint32_t>();
+    out->ktile_rows = tiling.tile_rows;
+    out->kranges = tiling.nranges;
+  }
+
+  // 4. per-level structure of the local records
+  SortedCoo sc;
+  rc = gather_levels(N, d_ind, perm, lorder, r0, nrec, tiled ? seg.as<uint32_t>() : nullptr, &sc);
+  if (rc != SPLATT_SUCCESS) return rc;
+  order.alloc(0);
+  tiled_order.alloc(0);
 
   DevBuf flag, nid, tmp, desc;
-  CK(flag.alloc(nnz * 4));
-  CK(nid.alloc(nnz * 4));
+  CK(flag.alloc(nrec * 4));
+  CK(nid.alloc(nrec * 4));
   const int stride = N - 2;
   CK(desc.alloc(std::max<uint64_t>(out->nchunks, 1) * stride * 4));
   size_t held = 0;
@@ -284,34 +382,33 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
     if (rc != SPLATT_SUCCESS) { spb200_free_stream(out); return rc; }
     out->nnodes[l] = nn;
     if (l <= N - 3) {
-      // +1 pad so a one-past-the-end prefetch stays in bounds
+      // +1 pad so a one-past-the-end read stays in bounds
       void * up = nullptr;
       cudaError_t e = cudaMalloc(&up, (nn + 1) * 4);
       if (e != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
       cudaMemset(up, 0, (nn + 1) * 4);
       out->up[l] = static_cast<uint32_t *>(up);
       held += (nn + 1) * 4;
-      if (nnz) {
-        k_scatter_nodes<<<nblk(nnz), 256>>>(sc.dl.as<uint8_t>(), l, nid.as<uint32_t>(),
-                                            sc.sidx[l].as<uint32_t>(), nnz, out->up[l], nullptr,
-                                            nullptr, nullptr);
-        if (out->nchunks)
-          k_desc<<<nblk(out->nchunks), 256>>>(nid.as<uint32_t>(), nnz, c0, out->nchunks, l, stride,
-                                              desc.as<uint32_t>());
+      if (nrec) {
+        k_scatter_nodes<<<nblk(nrec), 256>>>(sc.dl.as<uint8_t>(), l, nid.as<uint32_t>(),
+                                             sc.sidx[l].as<uint32_t>(), nrec, out->up[l], nullptr,
+                                             nullptr, nullptr);
+        k_desc<<<nblk(out->nchunks), 256>>>(nid.as<uint32_t>(), nrec, 0, out->nchunks, l, stride,
+                                            desc.as<uint32_t>());
       }
     }
   }
-  out->nnodes[N - 1] = nnz;
+  out->nnodes[N - 1] = nrec;
   {
     void * rec = nullptr;
-    cudaError_t e = cudaMalloc(&rec, std::max<uint64_t>(out->nrec, 1) * sizeof(SpRec));
+    cudaError_t e = cudaMalloc(&rec, std::max<uint64_t>(nrec, 1) * sizeof(SpRec));
     if (e != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
     out->rec = static_cast<SpRec *>(rec);
-    held += out->nrec * sizeof(SpRec);
-    if (out->nrec)
-      k_fill_rec<<<nblk(out->nrec), 256>>>(d_vals, sc.order_ptr(), sc.sidx[N - 1].as<uint32_t>(),
-                                           sc.sidx[N - 2].as<uint32_t>(), sc.dl.as<uint8_t>(), N,
-                                           nnz, r0, out->nrec, out->rec);
+    held += nrec * sizeof(SpRec);
+    if (nrec)
+      k_fill_rec<<<nblk(nrec), 256>>>(d_vals, sc.order.as<uint32_t>(), sc.sidx[N - 1].as<uint32_t>(),
+                                      sc.sidx[N - 2].as<uint32_t>(), sc.dl.as<uint8_t>(), N, nrec, 0,
+                                      nrec, out->rec);
   }
   held += desc.bytes;
   out->desc = static_cast<uint32_t *>(desc.release());
@@ -357,9 +454,13 @@ int spb200_build_host_csf(int N, const uint64_t * dims, uint64_t nnz,
   if (!csf->pt) return SPLATT_ERROR_NOMEMORY;
   csf_sparsity * pt = csf->pt;
 
-  SortedCoo sc;
-  int rc = sort_coo(N, dims, nnz, d_ind, perm, false, &sc);
+  DevBuf order;
+  int rc = sort_order(N, dims, nnz, d_ind, perm, false, &order);
   if (rc != SPLATT_SUCCESS) return rc;
+  SortedCoo sc;
+  rc = gather_levels(N, d_ind, perm, order.p ? order.as<uint32_t>() : nullptr, 0, nnz, nullptr, &sc);
+  if (rc != SPLATT_SUCCESS) return rc;
+  order.alloc(0);
 
   // leaves
   pt->nfibs[N - 1] = nnz;
@@ -370,7 +471,7 @@ int spb200_build_host_csf(int N, const uint64_t * dims, uint64_t nnz,
     DevBuf sv;
     CK(sv.alloc(nnz * 8));
     if (nnz) {
-      k_gather_f64<<<nblk(nnz), 256>>>(d_vals, sc.order_ptr(), nnz, sv.as<double>());
+      k_gather_f64<<<nblk(nnz), 256>>>(d_vals, sc.order.as<uint32_t>(), nnz, sv.as<double>());
       CK(cudaMemcpy(pt->vals, sv.p, nnz * 8, cudaMemcpyDeviceToHost));
     }
   }

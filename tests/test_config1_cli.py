@@ -1,0 +1,46 @@
+"""BASELINE config 1: the UNMODIFIED reference CLI on a small 3-mode .tns, rank 16, one CPU
+thread (reference plumbing, no GPU) -- proves the oracle build is a working SPLATT."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def _write_tns(path, ind, vals):
+    with open(path, "w") as f:
+        for n in range(len(vals)):
+            f.write(" ".join(str(int(ind[m][n]) + 1) for m in range(ind.shape[0])))   # 1-indexed
+            f.write(f" {float(vals[n])!r}\n")
+
+
+@pytest.mark.skipif(not ref.CLI_PATH.exists(), reason="oracle/_ref/splatt not built")
+def test_reference_cli_cpd_on_med_fixture(tmp_path):
+    z = np.load(GOLD / "med.npz")
+    tns = tmp_path / "med.tns"
+    _write_tns(tns, z["ind"], z["vals"])
+    r = subprocess.run([str(ref.CLI_PATH), "cpd", str(tns), "-r", "16", "-t", "1", "--seed", "1",
+                        "--nowrite", "-i", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "DIMS=2425x10816x29567" in out and "NNZ=100000" in out
+    fits = [float(x) for x in re.findall(r"fit = ([0-9.]+)", out)]
+    assert len(fits) == 5
+    assert abs(fits[-1] - 0.00087) < 2e-5          # fit 0.00087 after 5 its
+    assert "Final fit" in out
+
+
+@pytest.mark.skipif(not ref.CLI_PATH.exists(), reason="oracle/_ref/splatt not built")
+def test_reference_cli_small_fixture(tmp_path):
+    z = np.load(GOLD / "small.npz")
+    tns = tmp_path / "small.tns"
+    _write_tns(tns, z["ind"], z["vals"])
+    r = subprocess.run([str(ref.CLI_PATH), "cpd", str(tns), "-r", "2", "-t", "1", "--seed", "1",
+                        "--nowrite", "-i", "3"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "DIMS=2x3x2" in r.stdout and "NNZ=6" in r.stdout

@@ -171,6 +171,33 @@ def test_engine_device_path(S, refmod, name, layout):
     T.free()
 
 
+@pytest.mark.parametrize("name", ["t3_mid", "t3_long_fibers", "t3_skew", "t4", "t5"])
+@pytest.mark.parametrize("ktile", [1, 7, 64])
+def test_leaf_tiled_streams(S, refmod, name, ktile):
+    """Leaf-tile re-ordered streams (the L1-reuse layout) give the same MTTKRP, for the
+    root kernels and for the internal/leaf kernels, sharded or not."""
+    import torch
+    dims, inds, vals = _tensor(name)
+    R = 16
+    mats = factor_mats(dims, R)
+    _, gold = _gold(refmod, dims, inds, vals, mats)
+    dmats = [torch.from_numpy(m).cuda() for m in mats]
+    for layout in (0, 1):
+        for world in (1, 3):
+            shards = [S.Tensor.from_coo(dims, inds, vals, layout=layout, csf_alloc=0, shard_rank=r,
+                                        shard_count=world, ncolumns_hint=R, ktile=ktile)
+                      for r in range(world)]
+            for m in range(len(dims)):
+                acc = torch.zeros((dims[m], R), dtype=torch.float64, device="cuda")
+                for s in shards:
+                    out = torch.empty_like(acc)
+                    s.mttkrp(m, dmats, out)
+                    acc += out
+                assert rel_fro(acc.cpu().numpy(), gold[m]) < TOL, (name, ktile, layout, world, m)
+            for s in shards:
+                s.free()
+
+
 def test_sharded_partials_sum_to_whole(S, refmod):
     """shard_count > 1: per-shard partial outputs add up to the full MTTKRP
     (what the NCCL all-reduce does across ranks)."""

@@ -428,6 +428,12 @@ def run_ours(args):
                 "peak_source": how, "alg_bytes_per_launch": alg,
                 "launch_ms": k_ms, "traffic": ncu_traffic(),
                 "per_mode_ms": [float(np.mean(k)) for k in kern_ms],
+                "gather_path": {
+                    "bytes_per_launch": int(info[0]["nfibs"][-1] * RANK * 8 +
+                                            info[0]["nfibs"][-2] * RANK * 8),
+                    "note": "factor rows that must cross L2->SM per launch (one leaf row per "
+                            "nonzero + one parent row per fiber); ncu: lts2xbar 84.5 %, L1 data "
+                            "pipe 72 % busy -- this, not HBM, bounds the kernel (DESIGN.md 4.1)"},
                 "kernel_share_of_step": float(sum(np.mean(k) for k in kern_ms) / ms_per_step),
                 "launch_ms_includes": "memset + kernel" if fx is None else
                                       "kernel + group barrier + re-zero (fused exchange)",

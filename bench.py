@@ -282,6 +282,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the CUDA extension is the product, "
                            "there is no CPU fallback")

@@ -31,6 +31,13 @@ struct WsPriv {
   uint64_t out_rows_cap;
   cudaStream_t stream;
   double last_ms;
+  // SPLATT_B200_PIN=1: caller buffers seen by splatt_mttkrp_csf are page-locked on first
+  // sight (cudaHostRegister) so the H2D/D2H copies run at full PCIe rate; released in
+  // splatt_mttkrp_free_ws.  Opt-in because it assumes the buffers outlive the workspace
+  // (true for the reference's CPD driver, src/cpd.c:304-379).
+  bool pin;
+  int npinned;
+  void * pinned[4 * SPB200_MAXN];
 };
 
 int layout_from_env() {
@@ -40,8 +47,18 @@ int layout_from_env() {
   return SPLATT_B200_LAYOUT_ALLROOT;
 }
 
+void pin_once(WsPriv * w, void * p, size_t bytes) {
+  if (!w->pin || !p) return;
+  for (int i = 0; i < w->npinned; ++i)
+    if (w->pinned[i] == p) return;
+  if (w->npinned >= 4 * SPB200_MAXN) return;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) w->pinned[w->npinned++] = p;
+  else cudaGetLastError();   // already pinned / not registrable: copy works either way
+}
+
 void free_priv(WsPriv * w) {
   if (!w) return;
+  for (int i = 0; i < w->npinned; ++i) cudaHostUnregister(w->pinned[i]);
   for (int m = 0; m < SPB200_MAXN; ++m)
     if (w->d_mats[m]) cudaFree(w->d_mats[m]);
   if (w->d_out) cudaFree(w->d_out);
@@ -83,6 +100,10 @@ splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
   WsPriv * w = static_cast<WsPriv *>(calloc(1, sizeof(WsPriv)));
   if (!w) return nullptr;
   w->magic = kWsMagic;
+  {
+    const char * e = getenv("SPLATT_B200_PIN");
+    w->pin = e && atoi(e) != 0;
+  }
   const int N = (int)tensors[0].nmodes;
   w->N = N;
   for (int m = 0; m < N; ++m) w->dims[m] = tensors[0].dims[m];
@@ -162,11 +183,13 @@ void splatt_mttkrp_csf(splatt_csf const * const tensors, splatt_b200_matrix_t **
   cudaError_t e = cudaSuccess;
   for (int m = 0; m < N && e == cudaSuccess; ++m) {
     if (m == (int)mode) continue;                      // never read (may alias the output)
+    pin_once(w, mats[m]->vals, w->dims[m] * J * sizeof(double));
     e = h2d_matrix(w->d_mats[m], w->ldm, mats[m]->vals, w->dims[m], J, w->stream);
   }
   int rc = SPLATT_SUCCESS;
   if (e == cudaSuccess)
     rc = splatt_b200_mttkrp(w->T, (int)mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, w->stream);
+  pin_once(w, M->vals, w->dims[mode] * J * sizeof(double));
   if (e == cudaSuccess && rc == SPLATT_SUCCESS)
     e = d2h_matrix(M->vals, w->d_out, w->ldm, w->dims[mode], J, w->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);

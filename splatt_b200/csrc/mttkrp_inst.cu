@@ -7,12 +7,16 @@
 #endif
 
 int spb200_root_batch();
+int spb200_root_minb();
 
 namespace spb200 {
 
-template <int N, int L, int KIND, int BATCH, bool KT = false, bool MC = false>
+template <int N, int L, int KIND, int BATCH, bool KT = false, bool MC = false, int MINB = 0>
 static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
-  auto kern = mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC>;
+  auto kern = [] {
+    if constexpr (MINB == 0) return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC>;
+    else return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC, MINB>;
+  }();
   static int occ = 0;   // per-variant, set once
   if (occ == 0) {
     SPB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -41,6 +45,10 @@ static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStrea
       if (spb200_root_batch() >= 8) return launch_variant<N, L, SPB200_KIND_ROOT, 8>(args, num_sms, stream);
       if (spb200_root_batch() == 2) return launch_variant<N, L, SPB200_KIND_ROOT, 2>(args, num_sms, stream);
       if (args.ktiled) return launch_variant<N, L, SPB200_KIND_ROOT, 4, true>(args, num_sms, stream);
+      if constexpr (N >= 4) {
+        if (spb200_root_minb() == 3)
+          return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, false, 3>(args, num_sms, stream);
+      }
       return launch_variant<N, L, SPB200_KIND_ROOT, 4>(args, num_sms, stream);
     case SPB200_KIND_INTL: return launch_variant<N, L, SPB200_KIND_INTL, 4>(args, num_sms, stream);
     default:               return launch_variant<N, L, SPB200_KIND_LEAF, 4>(args, num_sms, stream);

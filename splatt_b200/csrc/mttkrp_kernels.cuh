@@ -159,8 +159,8 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
   }
 }
 
-template <int N, int L, int KIND, int BATCH, bool KT, bool MC>
-__global__ void __launch_bounds__(kThreads, ((BATCH >= 8 || N >= 4) ? 2 : 3))
+template <int N, int L, int KIND, int BATCH, bool KT, bool MC, int MINB = ((BATCH >= 8 || N >= 4) ? 2 : 3)>
+__global__ void __launch_bounds__(kThreads, MINB)
 mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
   constexpr int G  = 32 / L;            // groups per warp

@@ -24,6 +24,15 @@ int launch_n7(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n8(int, const MttkrpArgs &, int, cudaStream_t);
 }  // namespace spb200
 
+int spb200_root_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char * e = getenv("SPLATT_B200_MINB");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int num_sms_of_current_device() {
   static int cached[64] = {0};
   int dev = 0;

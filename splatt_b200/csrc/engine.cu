@@ -178,8 +178,6 @@ int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
     // times by the nonzeros one SM processes (otherwise every row is fetched once
     // anyway) and the leaf factor does not already fit in L1.
     StreamTiling tiling;
-    const bool is_root_stream = true;   // decided per plan below; tiling is only used by root kernels
-    (void)is_root_stream;
     // Measured on config 2: without a CTA-wide barrier per tile the lane
     // groups of an SM drift apart by several tiles, the L1 working set never shrinks and
     // the extra segment boundaries only cost REDs -- so the automatic mode stays off and the

@@ -28,7 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-O3",
 
 def _units():
     units = []
-    for n in range(3, 9):
+    for n in range(2, 9):
         units.append((f"mttkrp_inst_n{n}", CSRC / "mttkrp_inst.cu", [f"-DSPB200_INST_N={n}"]))
     for name in ("mttkrp_launch", "stream_build", "engine", "dropin", "cpd"):
         units.append((name, CSRC / f"{name}.cu", []))

@@ -247,7 +247,7 @@ int splatt_b200_tensor_from_coo(int nmodes, uint64_t const * dims, uint64_t nnz,
                                 uint32_t const * const * ind, double const * vals, int on_device,
                                 int csf_alloc, splatt_b200_build_opts const * bopts,
                                 splatt_b200_tensor ** out) {
-  if (!out || !dims || nmodes < 3 || nmodes > SPB200_MAXN || (nnz && (!ind || !vals))) {
+  if (!out || !dims || nmodes < 2 || nmodes > SPB200_MAXN || (nnz && (!ind || !vals))) {
     fprintf(stderr, "SPLATT: splatt_b200_tensor_from_coo: bad arguments\n");
     return SPLATT_ERROR_BADINPUT;
   }
@@ -301,8 +301,8 @@ int splatt_b200_tensor_from_csf(splatt_csf const * tensors, int csf_alloc,
                                 splatt_b200_build_opts const * bopts, splatt_b200_tensor ** out) {
   if (!tensors || !out) return SPLATT_ERROR_BADINPUT;
   const int N = (int)tensors[0].nmodes;
-  if (N < 3 || N > SPB200_MAXN) {
-    fprintf(stderr, "SPLATT: the B200 engine supports 3..%d modes (got %d)\n", SPB200_MAXN, N);
+  if (N < 2 || N > SPB200_MAXN) {
+    fprintf(stderr, "SPLATT: the B200 engine supports 2..%d modes (got %d)\n", SPB200_MAXN, N);
     return SPLATT_ERROR_BADINPUT;
   }
   int ncsf;

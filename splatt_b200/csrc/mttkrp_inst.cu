@@ -1,4 +1,4 @@
-// Instantiation unit: compiled once per mode count (-DSPB200_INST_N=3..8) so the
+// Instantiation unit: compiled once per mode count (-DSPB200_INST_N=2..8) so the
 // 6 x 4 x 3 kernel variants build in parallel.
 #include "mttkrp_kernels.cuh"
 

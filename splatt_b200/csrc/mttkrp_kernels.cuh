@@ -123,7 +123,7 @@ __device__ __forceinline__ double2 mul2(double2 a, double2 b) {
 template <int N, bool MC>
 __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q, const double2 b,
                                             const double2 r, const double2 r2,
-                                            double2 (&acc)[N - 1], uint32_t (&pos)[N - 2],
+                                            double2 (&acc)[N - 1], uint32_t (&pos)[(N > 2) ? N - 2 : 1],
                                             const char * const (&mbase)[N], char * obase,
                                             uint32_t pitch) {
   const double2  zero2 = make_double2(0.0, 0.0);
@@ -162,7 +162,7 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
 template <int N, int L, int KIND, int BATCH, bool KT, bool MC, int MINB = ((BATCH >= 8 || N >= 4) ? 2 : 3)>
 __global__ void __launch_bounds__(kThreads, MINB)
 mttkrp_stream_kernel(const MttkrpArgs a) {
-  static_assert(N >= 3 && N <= SPB200_MAXN, "3..8 modes");
+  static_assert(N >= 2 && N <= SPB200_MAXN, "2..8 modes");
   constexpr int G  = 32 / L;            // groups per warp
   constexpr int SU = kStageRecs / G;    // records per group per stage
 
@@ -225,11 +225,14 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
 
   // Traversal state.
   const double2 zero2 = make_double2(0.0, 0.0);
+  constexpr int NP = (N > 2) ? N - 2 : 1;
   double2       acc[N - 1];   // partial sums of levels 0..N-2 (levels >= outdepth)
   double2       pre[N - 1];   // Hadamard prefixes of levels 0..N-2 (levels < outdepth)
-  uint32_t      pos[N - 2];   // current node at levels 0..N-3
+  uint32_t      pos[NP];      // current node at levels 0..N-3
 #pragma unroll
   for (int l = 0; l < N - 1; ++l) { acc[l] = zero2; pre[l] = zero2; }
+#pragma unroll
+  for (int l = 0; l < NP; ++l) pos[l] = 0u;
 #pragma unroll
   for (int l = 0; l < N - 2; ++l) pos[l] = T ? a.desc[cb * (N - 2) + l] : 0u;
   uint32_t  pc = N - 1;        // close count of the previous record
@@ -252,7 +255,27 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
     __syncwarp();
 
     if (act) {
-      if constexpr (KIND == SPB200_KIND_ROOT) {
+      if constexpr (N == 2) {
+        // Matrices (2 modes): the record's parent IS the root row.  Root output:
+        // out[root] += sum v * U_leaf[k]  (sparse x dense);  leaf output: out[k] += v * U_root[root].
+        // reference: the generic kernels with nmodes == 2, src/mttkrp.c:668-732 / :860-943.
+        for (uint32_t n = 0; n < cnt; ++n) {
+          const uint4    q   = *reinterpret_cast<const uint4 *>(&buf[n]);
+          const double   v   = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
+          const uint32_t par = q.w & SPB200_IDX_MASK;
+          if constexpr (KIND == SPB200_KIND_ROOT) {
+            acc[0] = fma2(v, ld_row(mbase[1], q.z, pitch), acc[0]);
+            if (q.w >> SPB200_IDX_BITS) {
+              if constexpr (MC) red_row_mc(obase, par, pitch, acc[0]);
+              else red_row(obase, par, pitch, acc[0]);
+              acc[0] = zero2;
+            }
+          } else {
+            const double2 row = ld_row(mbase[0], par, pitch);
+            red_row(obase, q.z, pitch, make_double2(v * row.x, v * row.y));
+          }
+        }
+      } else if constexpr (KIND == SPB200_KIND_ROOT) {
         uint32_t n0 = 0;
         // full batches: all gathers of BATCH records are in flight before the first FMA
         for (; n0 + BATCH <= cnt; n0 += BATCH) {

@@ -16,6 +16,7 @@ int spb200_root_batch() {
 }
 
 namespace spb200 {
+int launch_n2(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n3(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n4(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n5(int, const MttkrpArgs &, int, cudaStream_t);
@@ -50,8 +51,8 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
                          const double * const * d_mats_by_mode, double * d_out,
                          uint64_t out_rows, cudaStream_t stream, bool multicast_out) {
   const int N = s.nmodes;
-  if (N < 3 || N > SPB200_MAXN) {
-    fprintf(stderr, "SPLATT: MTTKRP supports 3..%d modes (got %d)\n", SPB200_MAXN, N);
+  if (N < 2 || N > SPB200_MAXN) {
+    fprintf(stderr, "SPLATT: MTTKRP supports 2..%d modes (got %d)\n", SPB200_MAXN, N);
     return SPLATT_ERROR_BADINPUT;
   }
   if (ncolumns <= 0 || ldm < ncolumns + (ncolumns & 1) || (ldm & 1)) {
@@ -72,7 +73,7 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
 
   MttkrpArgs a;
   a.rec = s.rec;
-  for (int l = 0; l < SPB200_MAXN - 2; ++l) a.up[l] = (l <= N - 3) ? s.up[l] : nullptr;
+  for (int l = 0; l < SPB200_MAXN - 2; ++l) a.up[l] = (l <= N - 3) ? s.up[l] : nullptr;   // none for N = 2
   a.desc = s.desc;
   for (int l = 0; l < SPB200_MAXN; ++l) a.mats[l] = (l < N) ? d_mats_by_mode[s.perm[l]] : nullptr;
   a.out      = d_out;
@@ -90,6 +91,7 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
     a.ncols = (rpad - c0 < 64) ? (rpad - c0) : 64;
     int rc;
     switch (N) {
+      case 2:  rc = spb200::launch_n2(kind, a, num_sms, stream); break;
       case 3:  rc = spb200::launch_n3(kind, a, num_sms, stream); break;
       case 4:  rc = spb200::launch_n4(kind, a, num_sms, stream); break;
       case 5:  rc = spb200::launch_n5(kind, a, num_sms, stream); break;

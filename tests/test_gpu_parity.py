@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-11
 
 TENSORS = {
+    "t2_matrix": ((300, 500), 9000),
     "t3_small": ((13, 7, 11), 150),
     "t3_mid": ((300, 200, 400), 20000),
     "t3_long_fibers": ((50, 40, 3000), 30000),
@@ -100,7 +101,7 @@ def test_dropin_on_densetiled_reference_csf(S, refmod, name, tilelevel):
         csf.free()
 
 
-@pytest.mark.parametrize("name", ["t3_small", "t3_mid", "t4", "t5", "t8"])
+@pytest.mark.parametrize("name", ["t2_matrix", "t3_small", "t3_mid", "t4", "t5", "t8"])
 @pytest.mark.parametrize("alloc", [0, 1, 2])
 def test_csf_alloc_matches_reference(S, refmod, name, alloc):
     """splatt_b200_csf_alloc builds bit-identical CSF arrays to the reference's csf_alloc
@@ -150,7 +151,7 @@ def test_csf_alloc_gaps_keep_root_ids(S, refmod):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("name", ["t3_mid", "t3_skew", "t4", "t5"])
+@pytest.mark.parametrize("name", ["t2_matrix", "t3_mid", "t3_skew", "t4", "t5"])
 def test_engine_device_path(S, refmod, name, layout):
     """Device-resident API: COO -> fiber streams -> MTTKRP on torch CUDA tensors."""
     import torch
@@ -262,6 +263,26 @@ def test_cpd_als_rank_deficient_falls_back(S, refmod):
     fit, lam, fac = S.cpd_als(csf.ptr, 5, o, seed=2)
     assert np.isfinite(fit) and np.all(np.isfinite(lam))
     assert abs(fit - fit_ref) < 1e-6
+
+
+def test_pinned_dropin_path(S, refmod, monkeypatch):
+    """SPLATT_B200_PIN=1: caller buffers are page-locked on first sight; same results, and the
+    buffers are released with the workspace."""
+    monkeypatch.setenv("SPLATT_B200_PIN", "1")
+    dims, inds, vals = _tensor("t3_mid")
+    R = 8
+    mats = factor_mats(dims, R)
+    tt, gold = _gold(refmod, dims, inds, vals, mats)
+    o = refmod.default_opts()
+    csf = refmod.RefCsf(tt, o)
+    for rep in range(2):                      # a second workspace re-registers the same buffers
+        ws = S.MttkrpWorkspace(csf.ptr, R, o)
+        outs = [np.empty((d, R)) for d in dims]
+        for _ in range(2):
+            for m in range(3):
+                ws.mttkrp_csf(mats, m, outs[m])
+                assert rel_fro(outs[m], gold[m]) < TOL
+        ws.free()
 
 
 def test_alias_output_with_own_factor(S, refmod):
@@ -395,9 +416,11 @@ def test_empty_tensor_and_bad_input(S):
     T.mttkrp(0, mats, out)
     torch.cuda.synchronize()
     assert float(out.abs().sum()) == 0.0          # output is zeroed (src/mttkrp.c:1305)
-    with pytest.raises(S.SplattError) as ei:      # 2-mode tensors are outside the path
-        S.Tensor.from_coo([4, 5], [e, e], np.zeros(0))
+    with pytest.raises(S.SplattError) as ei:      # 1-mode "tensors" are rejected
+        S.Tensor.from_coo([4], [e], np.zeros(0))
     assert ei.value.code == A.SPLATT_ERROR_BADINPUT
+    with pytest.raises(S.SplattError):            # more than SPLATT_MAX_NMODES modes
+        S.Tensor.from_coo([2] * 9, [e] * 9, np.zeros(0))
     # odd leading dimension (rows would not be 16-byte aligned) is rejected by the library
     odd = [torch.ones(d, 5, dtype=torch.float64, device="cuda")[:, :3] for d in dims]
     with pytest.raises(S.SplattError) as ei:

@@ -452,7 +452,8 @@ def run_ours(args):
                     cv = nnz_total * RANK * NMODES / float(np.mean(step_s))
                     cpu = {"value": cv, "unit": "nnz*R/s", "cores": cores, "kind": "reference",
                            "sample": "full workload: 3 sweeps x 3 modes after 1 warm-up, reference "
-                                     "mttkrp_csf (OpenMP, TWOMODE, untiled, all host threads)"}
+                                     "mttkrp_csf (OpenMP, TWOMODE, untiled) at its fastest thread "
+                                     "count among 8..all host threads (cores = that count)"}
                 else:
                     cpu = {"value": None, "unit": "nnz*R/s", "cores": 0, "kind": "reference",
                            "sample": "oracle/_ref not present"}

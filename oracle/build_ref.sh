@@ -16,6 +16,8 @@
 # Outputs (git-ignored, shipped to the GPU box by gpurun):
 #   oracle/_ref/libsplatt_ref.so   reference library (all of src/*.c, OpenMP) + ref_driver.c
 #   oracle/_ref/splatt             reference CLI (src/cmds/*.c), BASELINE config #1
+#   oracle/_ref/splatt_gpu         the same CLI linked against libsplatt_b200.so for the
+#                                  MTTKRP symbols (drop-in proof, needs a GPU to run)
 #   oracle/_ref/gen/splatt/types.h generated type-width header
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -69,5 +71,24 @@ done
 wait
 gcc -fopenmp -o "$OUT/splatt" "${cmdobjs[@]}" "${objs[@]}" \
     "$BLASLIB" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -lm -lrt
+# The drop-in proof: the SAME unmodified reference CLI, but with the four MTTKRP
+# symbols of src/mttkrp.c renamed out of the way (objcopy, no source edits) so that
+# cpd.c / bench.c / the tests resolve splatt_mttkrp_csf, splatt_mttkrp_alloc_ws,
+# splatt_mttkrp_free_ws and splatt_mttkrp from libsplatt_b200.so (INTEGRATION.md,
+# option A).  `splatt_gpu cpd ...` = reference host code + B200 MTTKRP.
+B200LIB="$HERE/../splatt_b200/libsplatt_b200.so"
+if [ -f "$B200LIB" ]; then
+  objcopy --redefine-sym splatt_mttkrp_csf=splatt_mttkrp_csf_cpu \
+          --redefine-sym splatt_mttkrp=splatt_mttkrp_cpu \
+          --redefine-sym splatt_mttkrp_alloc_ws=splatt_mttkrp_alloc_ws_cpu \
+          --redefine-sym splatt_mttkrp_free_ws=splatt_mttkrp_free_ws_cpu \
+          "$OUT/obj/mttkrp.o" "$OUT/obj/mttkrp_cpu.o"
+  gpuobjs=()
+  for o in "${objs[@]}"; do
+    case "$o" in */mttkrp.o) gpuobjs+=("$OUT/obj/mttkrp_cpu.o");; *) gpuobjs+=("$o");; esac
+  done
+  gcc -fopenmp -o "$OUT/splatt_gpu" "${cmdobjs[@]}" "${gpuobjs[@]}" "$B200LIB" \
+      "$BLASLIB" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -Wl,-rpath,'$ORIGIN/../../splatt_b200' -lm -lrt
+fi
 rm -rf "$OUT/obj"
 echo "build_ref: built $OUT/libsplatt_ref.so and $OUT/splatt"

@@ -34,7 +34,7 @@ else:
 vals = torch.rand(nnz, device="cuda", dtype=torch.float64, generator=g)
 t0 = time.time()
 import os
-T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=1, verbosity=3,
+T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=int(os.environ.get("CSF_ALLOC", "1")), verbosity=3,
                       ncolumns_hint=R, ktile=int(os.environ.get("KTILE", "-1")))
 torch.cuda.synchronize()
 print(f"build {time.time()-t0:.2f}s  device MB {T.device_bytes/1e6:.0f}")

@@ -44,3 +44,33 @@ def test_reference_cli_small_fixture(tmp_path):
                         "--nowrite", "-i", "3"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stderr
     assert "DIMS=2x3x2" in r.stdout and "NNZ=6" in r.stdout
+
+
+GPU_CLI = ref.CLI_PATH.parent / "splatt_gpu"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not GPU_CLI.exists(), reason="oracle/_ref/splatt_gpu not built")
+@pytest.mark.parametrize("name,rank", [("med", 16), ("med4", 8), ("med5", 5)])
+def test_reference_cli_linked_against_libsplatt_b200(tmp_path, name, rank):
+    """The drop-in, end to end: the UNMODIFIED reference CLI (tt_read, csf_alloc, cpd_als_iterate,
+    LAPACK solve -- all reference code) with only its four MTTKRP symbols resolved from
+    libsplatt_b200.so (objcopy rename, INTEGRATION.md option A).  Same seed => the GPU-backed run
+    prints the same fit trajectory as the pure-CPU run."""
+    z = np.load(GOLD / f"{name}.npz")
+    tns = tmp_path / f"{name}.tns"
+    _write_tns(tns, z["ind"], z["vals"])
+    args = ["cpd", str(tns), "-r", str(rank), "-t", "2", "--seed", "3", "--nowrite", "-i", "6",
+            "--tol", "0"]
+    cpu = subprocess.run([str(ref.CLI_PATH)] + args, capture_output=True, text=True, timeout=300)
+    gpu = subprocess.run([str(GPU_CLI)] + args, capture_output=True, text=True, timeout=300)
+    assert cpu.returncode == 0 and gpu.returncode == 0, gpu.stderr
+    f_cpu = re.findall(r"fit = ([0-9.]+)  delta = ([-+0-9.e]+)", cpu.stdout)
+    f_gpu = re.findall(r"fit = ([0-9.]+)  delta = ([-+0-9.e]+)", gpu.stdout)
+    assert len(f_cpu) == 6 and len(f_gpu) == 6
+    for (a, da), (b, db) in zip(f_cpu, f_gpu):
+        assert abs(float(a) - float(b)) <= 1e-5           # printed to 5 decimals
+        assert abs(float(da) - float(db)) <= 1e-6 + 1e-3 * abs(float(da))
+    final_cpu = float(re.search(r"Final fit: ([0-9.]+)", cpu.stdout).group(1))
+    final_gpu = float(re.search(r"Final fit: ([0-9.]+)", gpu.stdout).group(1))
+    assert abs(final_cpu - final_gpu) <= 1e-5

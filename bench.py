@@ -232,6 +232,40 @@ def workload_config(n_gpus):
             "seed": SEED}
 
 
+def gather_probe_gbs(dev):
+    """Measured ceiling of the access pattern that bounds the kernel: random whole-row fp64
+    gathers (RANK columns) from a DIM-row matrix, nothing else (splatt_b200_gather_probe)."""
+    import ctypes as C
+    import torch
+    from splatt_b200 import _abi as A
+    lib = A.load()
+    n = 2 * NNZ_PER_GPU                      # one leaf + one parent row per nonzero
+    g = torch.Generator(device=dev).manual_seed(7)
+    idx = torch.randint(0, DIM, (n,), device=dev, dtype=torch.int32, generator=g)
+    mat = torch.rand(DIM, RANK, device=dev, dtype=torch.float64, generator=g)
+    sink = torch.zeros(8, device=dev, dtype=torch.float64)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = lib.splatt_b200_gather_probe(C.cast(C.c_void_p(mat.data_ptr()), A.val_p), RANK, RANK,
+                                          C.cast(C.c_void_p(idx.data_ptr()), C.POINTER(C.c_uint32)),
+                                          n, C.cast(C.c_void_p(sink.data_ptr()), A.val_p),
+                                          C.c_void_p(s))
+        assert rc == A.SPLATT_SUCCESS
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    return n * RANK * 8 / (ms * 1e-3) / 1e9, ms
+
+
 def cpd_iteration_times(S, csf, ind, vals, mats_h, ref_threads=None):
     """CPD-ALS seconds per iteration (the metric's second half): splatt_cpd_als of this
     library (MTTKRP + dense tail on the device) vs the reference's, same tensor, rank and
@@ -245,7 +279,8 @@ def cpd_iteration_times(S, csf, ind, vals, mats_h, ref_threads=None):
             S.cpd_als(csf.ptr, RANK, o, seed=SEED)
             return time.perf_counter() - t0
         ours(1)
-        out["ours_ms"] = (ours(22) - ours(2)) / 20 * 1e3
+        # 100 extra iterations (~0.13 s) dwarf the run-to-run noise of the set-up
+        out["ours_ms"] = (min(ours(110), ours(110)) - min(ours(10), ours(10))) / 100 * 1e3
     except Exception as e:  # pragma: no cover
         out["ours_error"] = str(e)
     try:
@@ -296,6 +331,10 @@ def run_ours(args):
     nnz_total = NNZ_PER_GPU * n_gpus
     dims = [DIM] * NMODES
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.3 s to deliver its first sample: start early;
+                                 # it runs through build, warm-up and the timed region
     # ---- build: identical tensor on every rank, each keeps its share of every stream
     ind, vals = make_coo_gpu(nnz_total, dev)
     t0 = time.time()
@@ -341,9 +380,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # runs through warm-up and the timed region
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         sweep()
@@ -368,7 +404,6 @@ def run_ours(args):
     barrier()
     wall_s = time.time() - wall0
     launches = S.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -419,24 +454,35 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t.item()) * 1e3
     e2e_value = nnz_total * RANK * NMODES / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None      # covers both timed regions (device + e2e)
 
     if rank == 0:
         # roofline of the dominant kernel: the root-stream kernel of mode 0
         peak, how = hbm_peak()
         k_ms = float(np.mean(kern_ms[0]))
         alg = info[0]["alg_bytes"]
+        gather_numbers = {}
+        try:
+            if world == 1:
+                peak_gbs, probe_ms = gather_probe_gbs(dev)
+                gb = info[0]["nfibs"][-1] * RANK * 8 + info[0]["nfibs"][-2] * RANK * 8
+                gather_numbers = {"achieved_GBps": gb / (k_ms * 1e-3) / 1e9,
+                                  "measured_peak_GBps": peak_gbs, "probe_ms": probe_ms,
+                                  "frac_of_measured_gather_peak": gb / (k_ms * 1e-3) / 1e9 / peak_gbs}
+        except Exception as e:  # pragma: no cover
+            gather_numbers = {"probe_error": str(e)}
         achieved = alg / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "mttkrp_stream_kernel<3,16,root> (mode 0)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": how, "alg_bytes_per_launch": alg,
                 "launch_ms": k_ms, "traffic": ncu_traffic(),
                 "per_mode_ms": [float(np.mean(k)) for k in kern_ms],
-                "gather_path": {
+                "gather_path": dict(gather_numbers, **{
                     "bytes_per_launch": int(info[0]["nfibs"][-1] * RANK * 8 +
                                             info[0]["nfibs"][-2] * RANK * 8),
                     "note": "factor rows that must cross L2->SM per launch (one leaf row per "
                             "nonzero + one parent row per fiber); ncu: lts2xbar 84.5 %, L1 data "
-                            "pipe 72 % busy -- this, not HBM, bounds the kernel (DESIGN.md 4.1)"},
+                            "pipe 72 % busy -- this, not HBM, bounds the kernel (DESIGN.md 4.1)"}),
                 "kernel_share_of_step": float(sum(np.mean(k) for k in kern_ms) / ms_per_step),
                 "launch_ms_includes": "memset + kernel" if fx is None else
                                       "kernel + group barrier + re-zero (fused exchange)",

@@ -350,6 +350,15 @@ int splatt_b200_mttkrp_multicast(
     double * mc_out,
     void * stream);
 
+/* Measurement aid: a pure gather kernel with the MTTKRP's access pattern (whole
+ * fp64 rows of a rows x ldm matrix at d_idx[0..nidx), 128-bit loads, eight rows in
+ * flight per lane group, no arithmetic).  bench.py times it to report a MEASURED
+ * ceiling for the L2->SM gather path next to the kernel's achieved rate.  Reads
+ * only the first min(ncolumns, 64) columns. */
+int splatt_b200_gather_probe(
+    double const * d_mat, int ncolumns, int ldm,
+    uint32_t const * d_idx, uint64_t nidx, double * d_sink, void * stream);
+
 /* Number of kernels the engine has launched in this process (bench.py's
  * gpu_launches evidence). */
 uint64_t splatt_b200_launch_count(void);

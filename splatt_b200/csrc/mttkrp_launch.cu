@@ -103,3 +103,53 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   }
   return SPLATT_SUCCESS;
 }
+
+
+// ---------------------------------------------------------------------------
+// Gather probe: the speed of light of the MTTKRP's dominant access pattern on
+// this GPU.  Every group of `lanes` lanes fetches whole rows (2 doubles per lane,
+// one LDG.128 each) of a rows x ld matrix at the indices idx[0..nidx), eight
+// rows in flight per group, and does nothing else.  bench.py times it to put a
+// MEASURED ceiling next to the kernel's achieved L2->SM gather rate.
+// ---------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256, 3)
+gather_probe_kernel(const double * __restrict__ mat, int ld, const uint32_t * __restrict__ idx,
+                    unsigned long long nidx, double * __restrict__ sink) {
+  constexpr int G = 32 / L;
+  const int lane = threadIdx.x & 31, grp = lane / L, gl = lane % L;
+  const unsigned long long ngroups = (unsigned long long)gridDim.x * (blockDim.x / 32) * G;
+  const unsigned long long g = ((unsigned long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * G + grp;
+  const unsigned long long b0 = g * nidx / ngroups, b1 = (g + 1) * nidx / ngroups;
+  const char * base = reinterpret_cast<const char *>(mat + 2 * gl);
+  const uint32_t pitch = (uint32_t)ld * 8u;
+  double2 acc = make_double2(0.0, 0.0);
+  unsigned long long n = b0;
+  for (; n + 8 <= b1; n += 8) {
+    uint32_t k[8];
+    double2  r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) k[u] = __ldg(&idx[n + u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      r[u] = __ldg(reinterpret_cast<const double2 *>(base + (unsigned long long)k[u] * pitch));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += r[u].x; acc.y += r[u].y; }
+  }
+  if (acc.x == 1.2345e300) sink[0] = acc.x + acc.y;   // keep the loads alive
+}
+
+extern "C" int splatt_b200_gather_probe(double const * d_mat, int ncolumns, int ldm,
+                                        uint32_t const * d_idx, uint64_t nidx, double * d_sink,
+                                        void * stream) {
+  if (!d_mat || !d_idx || !d_sink || ncolumns <= 0 || (ldm & 1) || ldm < ncolumns) return SPLATT_ERROR_BADINPUT;
+  const int grid = num_sms_of_current_device() * 3;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rp = ncolumns + (ncolumns & 1);
+  if (rp <= 8) gather_probe_kernel<4><<<grid, 256, 0, s>>>(d_mat, ldm, d_idx, nidx, d_sink);
+  else if (rp <= 16) gather_probe_kernel<8><<<grid, 256, 0, s>>>(d_mat, ldm, d_idx, nidx, d_sink);
+  else if (rp <= 32) gather_probe_kernel<16><<<grid, 256, 0, s>>>(d_mat, ldm, d_idx, nidx, d_sink);
+  else gather_probe_kernel<32><<<grid, 256, 0, s>>>(d_mat, ldm, d_idx, nidx, d_sink);
+  SPB200_CUDA_OK(cudaGetLastError());
+  return SPLATT_SUCCESS;
+}

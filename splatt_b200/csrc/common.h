@@ -57,12 +57,18 @@ struct FiberStream {
   size_t   bytes = 0;                      // HBM held
   uint32_t ktile_rows = 0;                 // >0: leaf-tile re-ordered (rows per tile)
   uint32_t kranges = 0;                    //     ... inside this many chunk-aligned ranges
+  // CTA-tiled variant (one range per CTA, leaf tile staged in shared memory):
+  uint32_t * seg_off = nullptr;            // [kranges * ntiles + 1] first record of every segment
+  uint32_t * rootid = nullptr;             // [nrec] root index of every record
+  uint32_t ntiles = 0;
+  uint64_t leaf_rows = 0;                  // rows of the leaf-mode factor
 };
 
 // Leaf-tile re-ordering request for spb200_build_stream (tile_rows == 0: off).
 struct StreamTiling {
   uint32_t tile_rows = 0;
   uint32_t nranges = 0;
+  bool     cta = false;      // build seg_off / rootid for the shared-memory tile kernel
 };
 
 enum { SPB200_KIND_ROOT = 0, SPB200_KIND_INTL = 1, SPB200_KIND_LEAF = 2 };
@@ -136,3 +142,10 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
                          const double * const * d_mats_by_mode, double * d_out,
                          uint64_t out_rows, cudaStream_t stream, bool multicast_out = false);
 extern unsigned long long g_spb200_launches;
+
+// mttkrp_tiled.cu -- 3-mode root kernel with the leaf factor staged tile by tile in smem
+bool spb200_tiled_applicable(const FiberStream & s, int kind, int ncolumns, int ldm);
+int spb200_launch_tiled_root3(const FiberStream & s, int ncolumns, int ldm, uint64_t leaf_rows,
+                              const double * leaf, const double * parent, double * d_out,
+                              cudaStream_t stream);
+uint32_t spb200_tiled_rows_for(int ncolumns);   // rows of a leaf tile that fit the kernel's smem

@@ -178,34 +178,42 @@ int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
     // times by the nonzeros one SM processes (otherwise every row is fetched once
     // anyway) and the leaf factor does not already fit in L1.
     StreamTiling tiling;
-    // Measured on config 2: without a CTA-wide barrier per tile the lane
-    // groups of an SM drift apart by several tiles, the L1 working set never shrinks and
-    // the extra segment boundaries only cost REDs -- so the automatic mode stays off and the
-    // layout is opt-in (ktile > 0, or SPLATT_B200_KTILE_AUTO=1 to apply the heuristic).
-    const char * auto_env = getenv("SPLATT_B200_KTILE_AUTO");
-    const bool allow_auto = auto_env && atoi(auto_env) != 0;
-    if (bo.ktile > 0 || (bo.ktile == 0 && allow_auto && bo.ncolumns_hint > 0)) {
+    // Two leaf-tiling layouts (both keep the stream valid for the generic kernels):
+    //  (a) CTA-tiled (opt-in, SPLATT_B200_TILED=1): one range per SM, leaf tiles staged in
+    //      shared memory by mttkrp_tiled.cu -- for 3-mode root streams when the rank is known
+    //      and every leaf row is re-used >= 3x by the nonzeros of one SM.  Measured slower
+    //      than the generic kernel on config 2: the L1 data pipe, which
+    //      serves shared-memory reads too, is the wall;
+    //  (b) L1-tiled (opt-in, ktile > 0): many small ranges, tiles kept hot in L1 only
+    //      statistically -- measured not to pay off.
+    {
       const uint64_t leaf_dim = dims[stream_perms[i].perm[N - 1]];
       uint64_t c0, c1;
       spb200_shard_chunks(dc.nnz, T->shard_rank, T->shard_count, &c0, &c1);
       const uint64_t local = std::min<uint64_t>(c1 * SPB200_CHUNK, dc.nnz) - c0 * SPB200_CHUNK;
-      uint32_t rows = 0;
-      if (bo.ktile > 0) rows = (uint32_t)bo.ktile;
-      else {
-        const uint64_t rowbytes = (uint64_t)(bo.ncolumns_hint + (bo.ncolumns_hint & 1)) * 8;
-        const char * e = getenv("SPLATT_B200_L1_TILE_KB");
-        const uint64_t budget = (e ? (uint64_t)atoi(e) : 64) * 1024;
-        rows = (uint32_t)std::max<uint64_t>(budget / std::max<uint64_t>(rowbytes, 8), 16);
-        const double reuse = (double)local / num_sms / (double)std::max<uint64_t>(leaf_dim, 1);
-        if (reuse < 3.0 || leaf_dim <= rows) rows = 0;
-      }
-      if (rows > 0) {
-        tiling.tile_rows = rows;
+      const char * te = getenv("SPLATT_B200_TILED");
+      const bool tiled_ok = te && atoi(te) >= 1;     // opt-in: measured slower than the generic kernel
+      if (bo.ktile > 0) {
+        tiling.tile_rows = (uint32_t)bo.ktile;
         tiling.nranges = (uint32_t)num_sms * 48u;
-        const uint64_t ntiles = (leaf_dim + rows - 1) / rows;
-        if ((uint64_t)tiling.nranges * ntiles >= 0xffffffffull ||
-            (bo.ktile == 0 && local < (uint64_t)tiling.nranges * 256))
-          tiling = StreamTiling();
+      } else if (bo.ktile == 0 && tiled_ok && N == 3 && bo.ncolumns_hint > 0 &&
+                 bo.ncolumns_hint <= 64) {
+        uint32_t rows = spb200_tiled_rows_for(bo.ncolumns_hint);
+        const char * re = getenv("SPLATT_B200_TILE_ROWS");          // testing / tuning
+        if (re && atoi(re) > 0) rows = std::min<uint32_t>(rows, (uint32_t)atoi(re));
+        const bool force = te && atoi(te) == 2;                      // testing: ignore the heuristics
+        const double reuse = (double)local / num_sms / (double)std::max<uint64_t>(leaf_dim, 1);
+        if (force ? (rows >= 1 && local > 0)
+                  : (rows >= 16 && leaf_dim > rows && reuse >= 3.0 &&
+                     local >= (uint64_t)num_sms * 4096)) {
+          tiling.tile_rows = rows;
+          tiling.nranges = (uint32_t)num_sms;
+          tiling.cta = true;
+        }
+      }
+      if (tiling.tile_rows) {
+        const uint64_t ntiles = (leaf_dim + tiling.tile_rows - 1) / tiling.tile_rows;
+        if ((uint64_t)tiling.nranges * ntiles >= 0x7fffffffull) tiling = StreamTiling();
       }
     }
     int rc = spb200_build_stream(N, dims, dc.nnz, dc.ind, dc.vals, stream_perms[i].perm,

@@ -255,6 +255,17 @@ int tile_local_order(const uint32_t * leaf_src, const uint32_t * lorder, uint64_
   return SPLATT_SUCCESS;
 }
 
+// seg_off[key] = first local record whose segment id is >= key (segment ids ascend).
+__global__ void k_seg_offsets(const uint32_t * __restrict__ seg, uint64_t n, uint32_t nkeys,
+                              uint32_t * __restrict__ seg_off) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t lo = (i == 0) ? 0u : seg[i - 1] + 1u;
+  const uint32_t hi = (i == n) ? nkeys : seg[i];          // keys in [lo, hi] start at i
+  if (i == n) { for (uint32_t k = lo; k <= nkeys; ++k) seg_off[k] = (uint32_t)n; return; }
+  for (uint32_t k = lo; k <= hi; ++k) seg_off[k] = (uint32_t)i;
+}
+
 __global__ void k_offset_iota(uint32_t * o, uint64_t n0, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) o[i] = (uint32_t)(n0 + i);
@@ -319,6 +330,8 @@ int scan_level(SortedCoo & sc, int level, DevBuf & flag, DevBuf & nid, DevBuf & 
 void spb200_free_stream(FiberStream * s) {
   if (!s) return;
   if (s->rec) cudaFree(s->rec);
+  if (s->seg_off) cudaFree(s->seg_off);
+  if (s->rootid) cudaFree(s->rootid);
   for (int l = 0; l < SPB200_MAXN; ++l)
     if (s->up[l]) cudaFree(s->up[l]);
   if (s->desc) cudaFree(s->desc);
@@ -333,6 +346,7 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
   out->nmodes = N;
   for (int l = 0; l < N; ++l) out->perm[l] = perm[l];
   out->nrec_total = nnz;
+  out->leaf_rows = dims[perm[N - 1]];
 
   // 1. whole-tensor CSF order
   DevBuf order;
@@ -370,12 +384,28 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
   order.alloc(0);
   tiled_order.alloc(0);
 
+  size_t held = 0;
+  if (tiled && tiling.cta) {
+    const uint32_t ntiles = (uint32_t)((dims[perm[N - 1]] + tiling.tile_rows - 1) / tiling.tile_rows);
+    const uint32_t nkeys = tiling.nranges * ntiles;
+    void * so = nullptr; void * ri = nullptr;
+    if (cudaMalloc(&so, ((size_t)nkeys + 1) * 4) != cudaSuccess ||
+        cudaMalloc(&ri, std::max<uint64_t>(nrec, 1) * 4) != cudaSuccess) {
+      if (so) cudaFree(so);
+      return SPLATT_ERROR_NOMEMORY;
+    }
+    out->seg_off = static_cast<uint32_t *>(so);
+    out->rootid = static_cast<uint32_t *>(ri);
+    out->ntiles = ntiles;
+    k_seg_offsets<<<nblk(nrec + 1), 256>>>(seg.as<uint32_t>(), nrec, nkeys, out->seg_off);
+    CK(cudaMemcpy(out->rootid, sc.sidx[0].as<uint32_t>(), nrec * 4, cudaMemcpyDeviceToDevice));
+    held += ((size_t)nkeys + 1) * 4 + nrec * 4;
+  }
   DevBuf flag, nid, tmp, desc;
   CK(flag.alloc(nrec * 4));
   CK(nid.alloc(nrec * 4));
   const int stride = N - 2;
   CK(desc.alloc(std::max<uint64_t>(out->nchunks, 1) * stride * 4));
-  size_t held = 0;
   for (int l = 0; l <= N - 2; ++l) {
     uint64_t nn = 0;
     rc = scan_level(sc, l, flag, nid, tmp, &nn);

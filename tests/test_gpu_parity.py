@@ -200,6 +200,35 @@ def test_leaf_tiled_streams(S, refmod, name, ktile):
                 s.free()
 
 
+@pytest.mark.parametrize("name", ["t3_small", "t3_mid", "t3_long_fibers", "t3_skew"])
+@pytest.mark.parametrize("rows", [1, 5, 37])
+@pytest.mark.parametrize("R", [2, 16, 32, 64])
+def test_cta_tiled_kernel(S, refmod, name, rows, R, monkeypatch):
+    """The shared-memory leaf-tile kernel (mttkrp_tiled.cu), forced on small tensors with
+    tiny tiles, sharded or not, against the reference's gold."""
+    import torch
+    monkeypatch.setenv("SPLATT_B200_TILED", "2")
+    monkeypatch.setenv("SPLATT_B200_TILE_ROWS", str(rows))
+    dims, inds, vals = _tensor(name)
+    mats = factor_mats(dims, R)
+    _, gold = _gold(refmod, dims, inds, vals, mats)
+    dmats = [torch.from_numpy(m).cuda() for m in mats]
+    for world in (1, 2):
+        shards = [S.Tensor.from_coo(dims, inds, vals, shard_rank=r, shard_count=world,
+                                    ncolumns_hint=R) for r in range(world)]
+        before = S.launch_count()
+        for m in range(3):
+            acc = torch.zeros((dims[m], R), dtype=torch.float64, device="cuda")
+            for s in shards:
+                out = torch.empty_like(acc)
+                s.mttkrp(m, dmats, out)
+                acc += out
+            assert rel_fro(acc.cpu().numpy(), gold[m]) < TOL, (name, rows, R, world, m)
+        assert S.launch_count() - before == 3 * world
+        for s in shards:
+            s.free()
+
+
 def test_sharded_partials_sum_to_whole(S, refmod):
     """shard_count > 1: per-shard partial outputs add up to the full MTTKRP
     (what the NCCL all-reduce does across ranks)."""

@@ -207,6 +207,9 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
       const uint32_t off = step * SU;
       const uint32_t cnt = (off < T) ? min(static_cast<uint32_t>(SU), T - off) : 0u;
       if (cnt) {
+        // generic-proxy accesses to this stage (record reads, the range-end patch) are
+        // ordered before the async-proxy refill
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(bar, cnt * 16u);
         tma_bulk_g2s(&srec[((warp * kStages + st) * G + grp) * SU], a.rec + rb + off, cnt * 16u,
                      bar);

@@ -60,6 +60,18 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
             ncolumns, ldm);
     return SPLATT_ERROR_BADINPUT;
   }
+  // rows are fetched with 128-bit loads: every matrix base must be 16-byte aligned
+  for (int m = 0; m < N; ++m) {
+    const double * p = d_mats_by_mode[m];
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) {
+      fprintf(stderr, "SPLATT: factor matrix %d is not 16-byte aligned\n", m);
+      return SPLATT_ERROR_BADINPUT;
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(d_out) & 15u) {
+    fprintf(stderr, "SPLATT: output matrix is not 16-byte aligned\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
   if (multicast_out) {
     // the caller zeroed every GPU's buffer and synchronised the group beforehand
     if (kind != SPB200_KIND_ROOT) {

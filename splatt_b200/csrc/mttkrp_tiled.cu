@@ -120,6 +120,7 @@ __global__ void __launch_bounds__((kTW + 1) * 32, 1) mttkrp_tiled_root3(const Ti
     if (lane == 0) {
       uint64_t * bar = &mybars[ij & 1u];
       if (cnt) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(bar, cnt * 16u);
         tma_bulk_g2s(myring + (ij & 1u) * kTRS, a.rec + rs, cnt * 16u, bar);
       } else {

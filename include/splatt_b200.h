@@ -332,6 +332,21 @@ int splatt_b200_mttkrp(
     double * d_out,
     void * stream);
 
+/* The same for a block of columns only: [col_begin, col_begin + col_count) (col_begin even).
+ * MTTKRP is independent per column, so a caller can pipeline column blocks against the
+ * PCIe copies of the corresponding factor columns (the drop-in symbols do exactly that
+ * when the host buffers are page-locked).  Only those columns of d_out are zeroed/written. */
+int splatt_b200_mttkrp_columns(
+    splatt_b200_tensor const * t,
+    int mode,
+    int ncolumns,
+    int ldm,
+    double const * const * d_mats,
+    double * d_out,
+    int col_begin,
+    int col_count,
+    void * stream);
+
 /* Fused MTTKRP + exchange for sharded tensors on one NVSwitch domain.  `mc_out` is
  * an NVLink MULTICAST address (CUDA multicast object / torch symmetric memory
  * `multicast_ptr`) bound to one dims[mode] x ldm buffer on every GPU of the

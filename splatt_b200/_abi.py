@@ -91,7 +91,7 @@ EXPORTS = [
     "splatt_b200_tensor_from_csf", "splatt_b200_tensor_from_coo", "splatt_b200_tensor_free",
     "splatt_b200_tensor_info", "splatt_b200_mode_info", "splatt_b200_csf_alloc",
     "splatt_b200_csf_free", "splatt_b200_mttkrp", "splatt_b200_launch_count",
-    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast", "splatt_b200_gather_probe",
+    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast", "splatt_b200_gather_probe", "splatt_b200_mttkrp_columns",
 ]
 
 _lib = None
@@ -155,6 +155,9 @@ def load() -> C.CDLL:
     lib.splatt_b200_mttkrp_multicast.restype = C.c_int
     lib.splatt_b200_mttkrp_multicast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp, val_p,
                                                  C.c_void_p]
+    lib.splatt_b200_mttkrp_columns.restype = C.c_int
+    lib.splatt_b200_mttkrp_columns.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp, val_p,
+                                               C.c_int, C.c_int, C.c_void_p]
     lib.splatt_b200_gather_probe.restype = C.c_int
     lib.splatt_b200_gather_probe.argtypes = [val_p, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                              C.c_uint64, val_p, C.c_void_p]

@@ -140,7 +140,8 @@ int spb200_build_host_csf(int nmodes, const uint64_t * dims, uint64_t nnz,
 int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
                          int ncolumns, int ldm,
                          const double * const * d_mats_by_mode, double * d_out,
-                         uint64_t out_rows, cudaStream_t stream, bool multicast_out = false);
+                         uint64_t out_rows, cudaStream_t stream, bool multicast_out = false,
+                         int col_begin = 0, int col_count = 0);
 extern unsigned long long g_spb200_launches;
 
 // mttkrp_tiled.cu -- 3-mode root kernel with the leaf factor staged tile by tile in smem

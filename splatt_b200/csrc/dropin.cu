@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <chrono>
+#include <algorithm>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -30,6 +31,8 @@ struct WsPriv {
   double * d_out;
   uint64_t out_rows_cap;
   cudaStream_t stream;
+  cudaStream_t copy_stream;       // PCIe copies of the column-block pipeline
+  cudaEvent_t ev_h2d[2], ev_k[2];
   double last_ms;
   // SPLATT_B200_PIN=1: caller buffers seen by splatt_mttkrp_csf are page-locked on first
   // sight (cudaHostRegister) so the H2D/D2H copies run at full PCIe rate; released in
@@ -63,6 +66,11 @@ void free_priv(WsPriv * w) {
     if (w->d_mats[m]) cudaFree(w->d_mats[m]);
   if (w->d_out) cudaFree(w->d_out);
   if (w->stream) cudaStreamDestroy(w->stream);
+  if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (w->ev_h2d[i]) cudaEventDestroy(w->ev_h2d[i]);
+    if (w->ev_k[i]) cudaEventDestroy(w->ev_k[i]);
+  }
   if (w->T) splatt_b200_tensor_free(w->T);
   w->magic = 0;
   free(w);
@@ -78,6 +86,52 @@ cudaError_t d2h_matrix(double * dst, const double * src, int ldm, uint64_t I, ui
                        cudaStream_t s) {
   if ((uint64_t)ldm == J) return cudaMemcpyAsync(dst, src, I * J * 8, cudaMemcpyDeviceToHost, s);
   return cudaMemcpy2DAsync(dst, J * 8, src, (size_t)ldm * 8, J * 8, I, cudaMemcpyDeviceToHost, s);
+}
+
+bool is_pinned(const void * p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Column-block pipeline (page-locked host buffers only): MTTKRP is independent per column,
+// so the factor columns of block 1 cross PCIe while the kernel runs on block 0, and block 0's
+// result goes back while the kernel runs on block 1.
+//   copy stream :  H2D blk0 | H2D blk1 |        D2H blk0 |          D2H blk1
+//   kernel stream:           kernel blk0        | kernel blk1
+cudaError_t pipelined_call(WsPriv * w, splatt_b200_matrix_t ** mats, int mode, uint64_t J, int * rc) {
+  const int N = w->N;
+  const int rpad = w->ldm;
+  const int half = ((rpad / 2) + 1) & ~1;                 // even split point
+  const int cb[3] = {0, half, rpad};
+  cudaError_t e = cudaSuccess;
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+    for (int m = 0; m < N && e == cudaSuccess && wcols; ++m) {
+      if (m == mode) continue;
+      e = cudaMemcpy2DAsync(w->d_mats[m] + c0, (size_t)w->ldm * 8, mats[m]->vals + c0, J * 8,
+                            wcols * 8, w->dims[m], cudaMemcpyHostToDevice, w->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(w->ev_h2d[b], w->copy_stream);
+  }
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaStreamWaitEvent(w->stream, w->ev_h2d[b], 0);
+    if (e != cudaSuccess) break;
+    *rc = splatt_b200_mttkrp_columns(w->T, mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, cb[b],
+                                     cb[b + 1] - cb[b], w->stream);
+    if (*rc != SPLATT_SUCCESS) return cudaSuccess;
+    e = cudaEventRecord(w->ev_k[b], w->stream);
+  }
+  splatt_b200_matrix_t * M = mats[SPLATT_B200_MAX_NMODES];
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+    e = cudaStreamWaitEvent(w->copy_stream, w->ev_k[b], 0);
+    if (e == cudaSuccess && wcols)
+      e = cudaMemcpy2DAsync(M->vals + c0, J * 8, w->d_out + c0, (size_t)w->ldm * 8, wcols * 8,
+                            w->dims[mode], cudaMemcpyDeviceToHost, w->copy_stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(w->copy_stream);
+  return e;
 }
 
 }  // namespace
@@ -139,6 +193,10 @@ splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
   w->out_rows_cap = maxdim;
   ok = ok && cudaMalloc(&w->d_out, maxdim * (size_t)w->ldm * 8) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&w->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&w->ev_k[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     fprintf(stderr, "SPLATT: out of device memory for MTTKRP workspace (%s)\n",
             cudaGetErrorString(cudaGetLastError()));
@@ -181,18 +239,33 @@ void splatt_mttkrp_csf(splatt_csf const * const tensors, splatt_b200_matrix_t **
   }
   auto t0 = std::chrono::steady_clock::now();
   cudaError_t e = cudaSuccess;
-  for (int m = 0; m < N && e == cudaSuccess; ++m) {
+  int rc = SPLATT_SUCCESS;
+  bool all_pinned = J >= 16;                           // narrow matrices: one block is enough
+  for (int m = 0; m < N; ++m) {
     if (m == (int)mode) continue;                      // never read (may alias the output)
     pin_once(w, mats[m]->vals, w->dims[m] * J * sizeof(double));
-    e = h2d_matrix(w->d_mats[m], w->ldm, mats[m]->vals, w->dims[m], J, w->stream);
+    all_pinned = all_pinned && is_pinned(mats[m]->vals);
   }
-  int rc = SPLATT_SUCCESS;
-  if (e == cudaSuccess)
-    rc = splatt_b200_mttkrp(w->T, (int)mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, w->stream);
   pin_once(w, M->vals, w->dims[mode] * J * sizeof(double));
-  if (e == cudaSuccess && rc == SPLATT_SUCCESS)
-    e = d2h_matrix(M->vals, w->d_out, w->ldm, w->dims[mode], J, w->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+  all_pinned = all_pinned && is_pinned(M->vals);
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char * pe = getenv("SPLATT_B200_PIPELINE");
+    use_pipe = (pe && atoi(pe) == 0) ? 0 : 1;
+  }
+  if (all_pinned && use_pipe) {
+    e = pipelined_call(w, mats, (int)mode, J, &rc);
+  } else {
+    for (int m = 0; m < N && e == cudaSuccess; ++m) {
+      if (m == (int)mode) continue;
+      e = h2d_matrix(w->d_mats[m], w->ldm, mats[m]->vals, w->dims[m], J, w->stream);
+    }
+    if (e == cudaSuccess)
+      rc = splatt_b200_mttkrp(w->T, (int)mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, w->stream);
+    if (e == cudaSuccess && rc == SPLATT_SUCCESS)
+      e = d2h_matrix(M->vals, w->d_out, w->ldm, w->dims[mode], J, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+  }
   if (e != cudaSuccess || rc != SPLATT_SUCCESS) {
     fprintf(stderr, "SPLATT: GPU MTTKRP failed (%s)\n", cudaGetErrorString(e));
     abort();

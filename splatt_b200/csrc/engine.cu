@@ -447,6 +447,19 @@ int splatt_b200_mttkrp(splatt_b200_tensor const * t, int mode, int ncolumns, int
                               d_out, t->dims[mode], static_cast<cudaStream_t>(stream));
 }
 
+int splatt_b200_mttkrp_columns(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
+                               double const * const * d_mats, double * d_out, int col_begin,
+                               int col_count, void * stream) {
+  if (!t || !d_mats || !d_out || mode < 0 || mode >= t->nmodes) {
+    fprintf(stderr, "SPLATT: splatt_b200_mttkrp_columns: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const ModePlan & p = t->plan[mode];
+  return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
+                              d_out, t->dims[mode], static_cast<cudaStream_t>(stream), false,
+                              col_begin, col_count);
+}
+
 int splatt_b200_mttkrp_multicast(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
                                  double const * const * d_mats, double * mc_out, void * stream) {
   if (!t || !d_mats || !mc_out || mode < 0 || mode >= t->nmodes) {

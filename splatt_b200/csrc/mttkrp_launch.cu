@@ -49,7 +49,8 @@ static int num_sms_of_current_device() {
 
 int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncolumns, int ldm,
                          const double * const * d_mats_by_mode, double * d_out,
-                         uint64_t out_rows, cudaStream_t stream, bool multicast_out) {
+                         uint64_t out_rows, cudaStream_t stream, bool multicast_out,
+                         int col_begin, int col_count) {
   const int N = s.nmodes;
   if (N < 2 || N > SPB200_MAXN) {
     fprintf(stderr, "SPLATT: MTTKRP supports 2..%d modes (got %d)\n", SPB200_MAXN, N);
@@ -78,13 +79,28 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
       fprintf(stderr, "SPLATT: multicast output needs a root-oriented stream (ALLROOT layout)\n");
       return SPLATT_ERROR_BADINPUT;
     }
-  } else {
-    SPB200_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * out_rows * ldm, stream));
+  }
+  const int rpad_all = ncolumns + (ncolumns & 1);
+  if (col_count <= 0) { col_begin = 0; col_count = rpad_all; }        // whole matrix
+  if ((col_begin & 1) || col_begin < 0 || col_begin + col_count > rpad_all + (col_count & 1) ||
+      col_begin >= rpad_all) {
+    fprintf(stderr, "SPLATT: bad column block [%d, %d) of %d\n", col_begin, col_begin + col_count,
+            rpad_all);
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const int col_end = (col_begin + col_count + 1) & ~1;               // even, <= rpad_all
+  if (!multicast_out) {
+    if (col_begin == 0 && col_end == rpad_all)
+      SPB200_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * out_rows * ldm, stream));
+    else
+      SPB200_CUDA_OK(cudaMemset2DAsync(d_out + col_begin, sizeof(double) * ldm, 0,
+                                       sizeof(double) * (col_end - col_begin), out_rows, stream));
   }
   if (s.nrec == 0) return SPLATT_SUCCESS;
 
   // leaf factor staged in shared memory (CTA-tiled stream, 3-mode root, one column pass)
-  if (!multicast_out && spb200_tiled_applicable(s, kind, ncolumns, ldm)) {
+  if (!multicast_out && col_begin == 0 && col_end == rpad_all &&
+      spb200_tiled_applicable(s, kind, ncolumns, ldm)) {
     static int use_tiled = -1;
     if (use_tiled < 0) {
       const char * e = getenv("SPLATT_B200_TILED_KERNEL");
@@ -109,11 +125,10 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   a.ktiled   = s.ktile_rows ? 1 : 0;
   a.multicast = multicast_out ? 1 : 0;
 
-  const int rpad    = ncolumns + (ncolumns & 1);
   const int num_sms = num_sms_of_current_device();
-  for (int c0 = 0; c0 < rpad; c0 += 64) {
+  for (int c0 = col_begin; c0 < col_end; c0 += 64) {
     a.col0  = c0;
-    a.ncols = (rpad - c0 < 64) ? (rpad - c0) : 64;
+    a.ncols = (col_end - c0 < 64) ? (col_end - c0) : 64;
     int rc;
     switch (N) {
       case 2:  rc = spb200::launch_n2(kind, a, num_sms, stream); break;

@@ -295,12 +295,13 @@ def test_cpd_als_rank_deficient_falls_back(S, refmod):
     assert abs(fit - fit_ref) < 1e-6
 
 
-def test_pinned_dropin_path(S, refmod, monkeypatch):
-    """SPLATT_B200_PIN=1: caller buffers are page-locked on first sight; same results, and the
-    buffers are released with the workspace."""
+@pytest.mark.parametrize("R", [8, 17, 32, 70])
+def test_pinned_dropin_path(S, refmod, monkeypatch, R):
+    """SPLATT_B200_PIN=1: caller buffers are page-locked on first sight; with page-locked
+    buffers and >= 16 columns the call runs as a two-block column pipeline (PCIe copies of one
+    block overlap the kernel of the other).  Same results; buffers released with the workspace."""
     monkeypatch.setenv("SPLATT_B200_PIN", "1")
     dims, inds, vals = _tensor("t3_mid")
-    R = 8
     mats = factor_mats(dims, R)
     tt, gold = _gold(refmod, dims, inds, vals, mats)
     o = refmod.default_opts()

@@ -397,30 +397,61 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        sweep()
-    barrier()
-    launches0 = S.launch_count()
-    step_ms, kern_ms = [], [[] for _ in range(NMODES)]
-    wall0 = time.time()
-    barrier()
-    for _ in range(args.steps):
+    # warm-up: at least W (>= 3) steps, and keep going (<= 2 s) until the step time has settled
+    # -- right after start-up the first ~100 ms of launches can run at half speed (clock /
+    # power-state ramp), which would otherwise land in the timed region
+    t_w0 = time.perf_counter()
+    recent, nwarm = [], 0
+    while True:
         flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        ke = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(NMODES)]
         e0.record()
-        sweep(ke)
+        sweep()
         e1.record()
         torch.cuda.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        for m in range(NMODES):
-            kern_ms[m].append(ke[m][0].elapsed_time(ke[m][1]))
+        recent.append(e0.elapsed_time(e1))
+        nwarm += 1
+        settled = len(recent) >= 10 and np.mean(recent[-5:]) <= 1.05 * min(recent)
+        done = nwarm >= max(args.warmup, 3) and (settled or time.perf_counter() - t_w0 > 2.0)
+        flag = torch.tensor([1.0 if done else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # every rank leaves together
+        if flag.item() > 0.5:
+            break
     barrier()
-    wall_s = time.time() - wall0
-    launches = S.launch_count() - launches0
+    def timed_region():
+        l0 = S.launch_count()
+        steps_ms, k_ms = [], [[] for _ in range(NMODES)]
+        w0 = time.time()
+        barrier()
+        for _ in range(args.steps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            ke = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                  for _ in range(NMODES)]
+            e0.record()
+            sweep(ke)
+            e1.record()
+            torch.cuda.synchronize()
+            steps_ms.append(e0.elapsed_time(e1))
+            for m in range(NMODES):
+                k_ms[m].append(ke[m][0].elapsed_time(ke[m][1]))
+        barrier()
+        return steps_ms, k_ms, time.time() - w0, S.launch_count() - l0
+
+    step_ms, kern_ms, wall_s, launches = timed_region()
+    # a timed region that ran far slower than the settled warm-up steps was disturbed (shared
+    # host, power-state ramp): measure once more and report the second measurement, flagged
+    disturbed = torch.tensor([1.0 if np.mean(step_ms) > 1.3 * min(recent) else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(disturbed, op=dist.ReduceOp.MAX)
+    remeasured = bool(disturbed.item() > 0.5)
+    if remeasured:
+        log(f"[rank {rank}] timed region {np.mean(step_ms):.3f} ms/step vs settled warm-up "
+            f"{min(recent):.3f}: re-measuring once")
+        step_ms, kern_ms, wall_s, launches = timed_region()
 
     total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -532,7 +563,7 @@ def run_ours(args):
             cpd = cpd_iteration_times(S, csf, ind, vals, mats_h,
                                       cpu.get("cores") if cpu and cpu.get("value") else None)
         line = {"metric": "MTTKRP nnz*R/sec per mode", "value": value, "unit": "nnz*R/s",
-                "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": nwarm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(workload_config(n_gpus), exchange=exchange),
@@ -545,6 +576,7 @@ def run_ours(args):
                 "roofline": roof,
                 "cpu_baseline": cpu,
                 "cpd_als_iteration": cpd,
+                "remeasured": remeasured,
                 "build_seconds": build_s, "wall_seconds_timed_region": wall_s,
                 "device_bytes": T.device_bytes}
         print(json.dumps(line))

@@ -365,6 +365,24 @@ int splatt_b200_mttkrp_multicast(
     double * mc_out,
     void * stream);
 
+/* The dense tail of one ALS mode update on the device -- the kernels splatt_cpd_als uses --
+ * as separate entry points, so a multi-GPU driver can interleave them with its exchange:
+ *   local MTTKRP (shard) -> sum over ranks -> splatt_b200_als_tail_update (replicated).
+ * Replaces, per call: mat_solve_normals src/matrix.c:529-606, mat_normalize :501-525,
+ * mat_aTa :414-455, p_calc_fit src/cpd.c:237-265.  All matrices are device pointers with
+ * leading dimension ldm; work is enqueued on the stream given at creation. */
+typedef struct splatt_b200_als_tail splatt_b200_als_tail;
+int  splatt_b200_als_tail_create(int nmodes, int ncolumns, int ldm, void * stream,
+                                 splatt_b200_als_tail ** out);
+void splatt_b200_als_tail_free(splatt_b200_als_tail * h);
+int  splatt_b200_als_tail_gram(splatt_b200_als_tail * h, int mode, double const * d_factor,
+                               uint64_t rows);
+int  splatt_b200_als_tail_update(splatt_b200_als_tail * h, int mode, double const * d_m1,
+                                 double * d_factor, uint64_t rows, int first_iteration);
+int  splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_factor,
+                              double const * d_last_m1, uint64_t rows, double ttnormsq,
+                              double * fit_out, double * lambda_out);
+
 /* Measurement aid: a pure gather kernel with the MTTKRP's access pattern (whole
  * fp64 rows of a rows x ldm matrix at d_idx[0..nidx), 128-bit loads, eight rows in
  * flight per lane group, no arithmetic).  bench.py times it to report a MEASURED

@@ -698,6 +698,77 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
   return SPLATT_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------
+// The device ALS tail as engine entry points, so that a multi-GPU driver can run
+//   local MTTKRP on its shard -> exchange -> (replicated) tail
+// with the same kernels splatt_cpd_als uses (splatt_b200/parallel.py:cpd_als_sharded).
+// ---------------------------------------------------------------------------
+struct splatt_b200_als_tail { DevTail t; };
+
+int splatt_b200_als_tail_create(int nmodes, int ncolumns, int ldm, void * stream,
+                                splatt_b200_als_tail ** out) {
+  if (!out || nmodes < 2 || nmodes > SPB200_MAXN || ncolumns < 1 || ncolumns > 128 ||
+      ldm < ncolumns) return SPLATT_ERROR_BADINPUT;
+  splatt_b200_als_tail * h = new splatt_b200_als_tail();
+  if (!h->t.alloc(nmodes, ncolumns, ldm, static_cast<cudaStream_t>(stream))) {
+    h->t.release();
+    delete h;
+    return SPLATT_ERROR_NOMEMORY;
+  }
+  *out = h;
+  return SPLATT_SUCCESS;
+}
+
+void splatt_b200_als_tail_free(splatt_b200_als_tail * h) {
+  if (!h) return;
+  h->t.release();
+  delete h;
+}
+
+// Gram of one factor (call once per factor before the first iteration).
+int splatt_b200_als_tail_gram(splatt_b200_als_tail * h, int mode, double const * d_factor,
+                              uint64_t rows) {
+  if (!h || mode < 0 || mode >= h->t.N) return SPLATT_ERROR_BADINPUT;
+  h->t.gram(d_factor, rows, mode);
+  return cudaGetLastError() == cudaSuccess ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+}
+
+// One mode update: d_m1 (the summed MTTKRP result) -> d_factor, lambda, Gram of the mode.
+int splatt_b200_als_tail_update(splatt_b200_als_tail * h, int mode, double const * d_m1,
+                                double * d_factor, uint64_t rows, int first_iteration) {
+  if (!h || mode < 0 || mode >= h->t.N) return SPLATT_ERROR_BADINPUT;
+  h->t.mode_step(d_m1, d_factor, rows, mode, first_iteration != 0);
+  return cudaGetLastError() == cudaSuccess ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+}
+
+// Fit after the last mode's update (reference: p_calc_fit src/cpd.c:237-265).  Synchronises
+// the stream; lambda_out (ncolumns doubles, host) may be NULL.
+int splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_factor,
+                             double const * d_last_m1, uint64_t rows, double ttnormsq,
+                             double * fit_out, double * lambda_out) {
+  if (!h || !fit_out) return SPLATT_ERROR_BADINPUT;
+  DevTail & t = h->t;
+  const int N = t.N, R = t.R;
+  const size_t nb = (size_t)N * R * R;
+  cudaMemsetAsync(t.inner, 0, sizeof(double), t.s);
+  k_inner<<<296, 256, 0, t.s>>>(d_last_factor, d_last_m1, rows, R, t.ld, t.lambda, t.inner);
+  g_spb200_launches += 1;
+  cudaMemcpyAsync(t.h_back, t.ata, nb * 8, cudaMemcpyDeviceToHost, t.s);
+  cudaMemcpyAsync(t.h_back + nb, t.lambda, R * 8, cudaMemcpyDeviceToHost, t.s);
+  cudaMemcpyAsync(t.h_back + nb + R, t.inner, 8, cudaMemcpyDeviceToHost, t.s);
+  if (cudaStreamSynchronize(t.s) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+  std::vector<std::vector<double>> ata(N, std::vector<double>((size_t)R * R));
+  for (int m = 0; m < N; ++m)
+    memcpy(ata[m].data(), t.h_back + (size_t)m * R * R, sizeof(double) * R * R);
+  const double * lambda = t.h_back + nb;
+  const double norm_mats = kruskal_norm(ata, lambda, N, R);
+  double residual = ttnormsq + norm_mats - 2 * t.h_back[nb + R];
+  if (residual > 0.) residual = std::sqrt(residual);
+  *fit_out = 1 - residual / std::sqrt(ttnormsq);
+  if (lambda_out) memcpy(lambda_out, lambda, sizeof(double) * R);
+  return SPLATT_SUCCESS;
+}
+
 void splatt_free_kruskal(splatt_kruskal * factored) {
   if (!factored) return;
   free(factored->lambda);

@@ -37,10 +37,13 @@ class FusedExchange:
 
     One symmetric-memory buffer per mode (dims[mode] x ldm fp64) is mapped on every GPU
     and bound to a multicast address; `mttkrp(mode, mats)` launches the root kernel with
-    `multimem.red.add.f64` reductions into that address, then one group barrier.  Buffers
-    are re-zeroed locally right after they are consumed; with one buffer per mode the
-    barrier that ends the next mode's call orders that zeroing before any peer's next
-    write, so a single barrier per call suffices (needs >= 2 modes, always true).
+    `multimem.red.add.f64` reductions into that address, then one group barrier.  A buffer
+    is re-zeroed locally by `release(mode)` once its result is consumed.  A peer may only
+    write into it again after that zeroing: some group barrier must lie between the
+    release and the buffer's next use.  In the ALS order (release right after each mode)
+    the barrier ending the next mode's call provides it for free -- one barrier per call;
+    otherwise `mttkrp` inserts the missing barrier itself (every rank takes the same
+    decision, so the extra barrier is collective).
 
     `available()` is False when the process group has no multicast support (then use
     `sharded_mttkrp`: local kernel + NCCL all-reduce)."""
@@ -69,12 +72,18 @@ class FusedExchange:
         except Exception as e:      # no symmetric memory in this environment
             self.ok = False
             self.error = f"{type(e).__name__}: {e}"
+        self._barriers = 0                       # group barriers issued so far
+        self._released_at = [-1] * tensor.nmodes  # barrier count when the buffer was last zeroed
         if self.ok:
             for b in self.bufs:
                 b.zero_()
             torch.cuda.synchronize()
-            self.hdls[0].barrier(channel=0)
+            self._barrier(0)
             torch.cuda.synchronize()
+
+    def _barrier(self, mode):
+        self.hdls[mode].barrier(channel=0)
+        self._barriers += 1
 
     def available(self) -> bool:
         return self.ok
@@ -89,15 +98,101 @@ class FusedExchange:
                 ptrs[m] = A.val_p()
             else:
                 ptrs[m] = C.cast(C.c_void_p(mats[m].data_ptr()), A.val_p)
+        if self._released_at[mode] == self._barriers:
+            self._barrier(mode)      # no barrier since this buffer was zeroed: order it now
         s = torch.cuda.current_stream().cuda_stream
         rc = lib.splatt_b200_mttkrp_multicast(
             self.t.h, mode, self.R, self.ldm, ptrs,
             C.cast(C.c_void_p(self.hdls[mode].multicast_ptr), A.val_p), C.c_void_p(s))
         if rc != A.SPLATT_SUCCESS:
             raise RuntimeError(f"splatt_b200_mttkrp_multicast failed ({rc})")
-        self.hdls[mode].barrier(channel=0)
+        self._barrier(mode)
         return self.bufs[mode]
 
     def release(self, mode):
         """Call when the result of `mode` has been consumed: re-zero it for its next use."""
         self.bufs[mode].zero_()
+        self._released_at[mode] = self._barriers
+
+
+def cpd_als_sharded(tensor, ncolumns, init_factors, ttnormsq, niters=50, tol=1e-5, fused=True,
+                    group=None, verbose=False):
+    """CPD-ALS over a sharded tensor: one process per GPU.
+
+    Per mode: MTTKRP of this rank's shard, summed over ranks (fused NVLink-multicast exchange
+    when available and `fused`, else NCCL all-reduce), then the dense tail replicated on every
+    rank with the same device kernels `splatt_cpd_als` uses (`splatt_b200_als_tail_*`).  The
+    iteration is the reference's (src/cpd.c:318-373).  Also runs unsharded (no process group).
+
+    init_factors: list of torch CUDA float64 (dims[m] x ncolumns) -- identical on every rank.
+    Returns (fit, lambda (numpy), factors (torch, unnormalised as left by the last iteration),
+             seconds per iteration list)."""
+    import time
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    lib = tensor.lib
+    N, R = tensor.nmodes, ncolumns
+    ldm = R + (R & 1)
+    dev = init_factors[0].device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    fx = None
+    if world > 1 and fused:
+        fx = FusedExchange(tensor, R, group)
+        if not fx.available():
+            fx = None
+    mats = []
+    for m in range(N):
+        a = torch.zeros((tensor.dims[m], ldm), dtype=torch.float64, device=dev)
+        a[:, :R] = init_factors[m]
+        mats.append(a)
+    outs = [torch.empty((tensor.dims[m], ldm), dtype=torch.float64, device=dev) for m in range(N)]
+    views = [a[:, :R] for a in mats]
+    stream = torch.cuda.current_stream().cuda_stream
+    h = C.c_void_p()
+    rc = lib.splatt_b200_als_tail_create(N, R, ldm, C.c_void_p(stream), C.byref(h))
+    if rc != A.SPLATT_SUCCESS:
+        raise RuntimeError(f"splatt_b200_als_tail_create failed ({rc})")
+
+    def ptr(t):
+        return C.cast(C.c_void_p(t.data_ptr()), A.val_p)
+    try:
+        for m in range(N):
+            lib.splatt_b200_als_tail_gram(h, m, ptr(mats[m]), tensor.dims[m])
+        fit = oldfit = 0.0
+        lam = np.zeros(R)
+        lam_c = (C.c_double * R)()
+        times = []
+        for it in range(niters):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for m in range(N):
+                if fx is not None:
+                    m1 = fx.mttkrp(m, mats)[:, :ldm]
+                else:
+                    tensor.mttkrp(m, mats, outs[m], ncolumns=R)
+                    m1 = all_reduce_output(outs[m], group)
+                rc = lib.splatt_b200_als_tail_update(h, m, ptr(m1), ptr(mats[m]), tensor.dims[m],
+                                                     1 if it == 0 else 0)
+                if rc != A.SPLATT_SUCCESS:
+                    raise RuntimeError("splatt_b200_als_tail_update failed")
+                last_m1 = m1
+                if fx is not None and m != N - 1:
+                    fx.release(m)
+            f = C.c_double()
+            rc = lib.splatt_b200_als_tail_fit(h, ptr(mats[N - 1]), ptr(last_m1), tensor.dims[N - 1],
+                                              float(ttnormsq), C.byref(f), lam_c)
+            if fx is not None:
+                fx.release(N - 1)
+            fit = f.value
+            lam = np.array(lam_c[:])
+            times.append(time.perf_counter() - t0)
+            if verbose:
+                print(f"  its = {it + 1:3d} ({times[-1]:.4f}s)  fit = {fit:.5f}  "
+                      f"delta = {fit - oldfit:+.4e}", flush=True)
+            if fit == 1.0 or (it > 0 and abs(fit - oldfit) < tol):
+                break
+            oldfit = fit
+        return fit, lam, [v.clone() for v in views], times
+    finally:
+        lib.splatt_b200_als_tail_free(h)

@@ -457,3 +457,54 @@ def test_empty_tensor_and_bad_input(S):
     with pytest.raises(S.SplattError) as ei:
         T.mttkrp(0, odd, torch.ones(4, 5, dtype=torch.float64, device="cuda")[:, :3])
     assert ei.value.code == A.SPLATT_ERROR_BADINPUT
+
+
+def _libc_rand_factors(dims, R, seed):
+    """The reference's factor initialisation: srand(seed), then mat_rand per mode in order
+    (src/cpd.c:36-40, src/util.c:15-23: two rand() draws per value)."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.srand(ctypes.c_uint(seed))
+    RAND_MAX = 2147483647
+    out = []
+    for d in dims:
+        a = np.empty((d, R))
+        flat = a.reshape(-1)
+        for x in range(flat.size):
+            v = 3.0 * (libc.rand() / RAND_MAX)
+            if libc.rand() % 2 == 0:
+                v *= -1
+            flat[x] = v
+        out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("spec", [((60, 50, 40), 6000, 6), ((30, 25, 20, 15), 5000, 5)])
+def test_sharded_cpd_driver_matches_splatt_cpd_als(S, refmod, spec):
+    """splatt_b200.parallel.cpd_als_sharded (MTTKRP -> exchange -> device tail through the
+    splatt_b200_als_tail_* entry points; here world = 1) walks the same trajectory as
+    splatt_cpd_als and as the compiled reference."""
+    import torch
+    from splatt_b200 import parallel
+    dims, inds, vals = random_coo(spec[0], spec[1], seed=3)
+    dims, inds, vals = cover_all_slices(dims, inds, vals)
+    R, seed, its = spec[2], 7, 8
+    o = refmod.default_opts()
+    o[0], o[3], o[1], o[4] = 1, its, 0.0, 0
+    tt = refmod.RefTensor.from_coo(dims, inds, vals)
+    csf = refmod.RefCsf(tt, o)
+    fit_ref, lam_ref, fac_ref = csf.cpd_als(R, seed=seed)
+    init = [torch.from_numpy(a).cuda() for a in _libc_rand_factors(dims, R, seed)]
+    T = S.Tensor.from_coo(dims, inds, vals)
+    fit, lam, fac, times = parallel.cpd_als_sharded(T, R, init, float(np.sum(vals * vals)),
+                                                   niters=its, tol=0.0)
+    assert len(times) == its
+    assert abs(fit - fit_ref) < 1e-8
+    # the reference post-processes (2-normalises factors into lambda, src/cpd.c:391-411)
+    lam_pp = lam.copy()
+    for m, a in enumerate(fac):
+        a = a.cpu().numpy()
+        nrm = np.sqrt((a * a).sum(axis=0))
+        lam_pp *= nrm
+        assert np.allclose(a / nrm, fac_ref[m], rtol=1e-5, atol=1e-8)
+    assert np.allclose(lam_pp, lam_ref, rtol=1e-6, atol=1e-9)

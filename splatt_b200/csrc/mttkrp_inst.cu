@@ -7,7 +7,6 @@
 #endif
 
 int spb200_root_batch();
-int spb200_root_minb();
 
 namespace spb200 {
 
@@ -43,12 +42,11 @@ static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStrea
     case SPB200_KIND_ROOT:
       if (args.multicast) return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, true>(args, num_sms, stream);
       if (spb200_root_batch() >= 8) return launch_variant<N, L, SPB200_KIND_ROOT, 8>(args, num_sms, stream);
-      if (spb200_root_batch() == 2) return launch_variant<N, L, SPB200_KIND_ROOT, 2>(args, num_sms, stream);
+      // deeper trees hold a third gathered row per record: two-record batches keep the
+      // kernel at 80 registers / 3 CTAs per SM (measured 1014 vs 1052 us on config 3)
+      if (spb200_root_batch() == 2 || (spb200_root_batch() == 0 && N >= 4))
+        return launch_variant<N, L, SPB200_KIND_ROOT, 2>(args, num_sms, stream);
       if (args.ktiled) return launch_variant<N, L, SPB200_KIND_ROOT, 4, true>(args, num_sms, stream);
-      if constexpr (N >= 4) {
-        if (spb200_root_minb() == 3)
-          return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, false, 3>(args, num_sms, stream);
-      }
       return launch_variant<N, L, SPB200_KIND_ROOT, 4>(args, num_sms, stream);
     case SPB200_KIND_INTL: return launch_variant<N, L, SPB200_KIND_INTL, 4>(args, num_sms, stream);
     default:               return launch_variant<N, L, SPB200_KIND_LEAF, 4>(args, num_sms, stream);

@@ -9,8 +9,8 @@ int spb200_root_batch() {
   static int v = -1;
   if (v < 0) {
     const char * e = getenv("SPLATT_B200_BATCH");
-    v = e ? atoi(e) : 0;   // 0 = per-kernel default (4)
-    if (v != 2 && v != 8) v = 4;
+    v = e ? atoi(e) : 0;   // 0 = per-kernel default (4 for 2-3 modes, 2 for deeper trees)
+    if (v != 2 && v != 3 && v != 4 && v != 8) v = 0;
   }
   return v;
 }
@@ -24,15 +24,6 @@ int launch_n6(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n7(int, const MttkrpArgs &, int, cudaStream_t);
 int launch_n8(int, const MttkrpArgs &, int, cudaStream_t);
 }  // namespace spb200
-
-int spb200_root_minb() {
-  static int v = -1;
-  if (v < 0) {
-    const char * e = getenv("SPLATT_B200_MINB");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
 
 static int num_sms_of_current_device() {
   static int cached[64] = {0};

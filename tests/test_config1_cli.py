@@ -1,5 +1,6 @@
 """BASELINE config 1: the UNMODIFIED reference CLI on a small 3-mode .tns, rank 16, one CPU
 thread (reference plumbing, no GPU) -- proves the oracle build is a working SPLATT."""
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -74,3 +75,36 @@ def test_reference_cli_linked_against_libsplatt_b200(tmp_path, name, rank):
     final_cpu = float(re.search(r"Final fit: ([0-9.]+)", cpu.stdout).group(1))
     final_gpu = float(re.search(r"Final fit: ([0-9.]+)", gpu.stdout).group(1))
     assert abs(final_cpu - final_gpu) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not GPU_CLI.exists(), reason="oracle/_ref/splatt_gpu not built")
+@pytest.mark.parametrize("name", ["med", "med4"])
+def test_reference_bench_harness_on_gpu(tmp_path, name):
+    """the reference's own MTTKRP benchmark driver (`splatt bench -a csf`,
+    src/bench.c:133-224 -- it forces ONEMODE + DENSETILE CSFs) running on the GPU engine through
+    the same link-time replacement, with `-w` dumping every mode's MTTKRP result
+    (csf_mode<N>.mat): the dumps must match the pure-CPU binary's."""
+    z = np.load(GOLD / f"{name}.npz")
+    tns = tmp_path / f"{name}.tns"
+    _write_tns(tns, z["ind"], z["vals"])
+    # the CLI seeds rand() with time(NULL) (src/cmds/splatt_bin.c:91): pin time() for both runs so
+    # that both binaries draw the same random factor matrices
+    shim_c = tmp_path / "time_shim.c"
+    shim_c.write_text("#include <time.h>\ntime_t time(time_t * t) { if (t) *t = 1234567; return 1234567; }\n")
+    shim = tmp_path / "time_shim.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(shim), str(shim_c)], check=True)
+    env = dict(os.environ, LD_PRELOAD=str(shim))
+    outs = {}
+    for tag, exe in (("cpu", ref.CLI_PATH), ("gpu", GPU_CLI)):
+        wd = tmp_path / tag
+        wd.mkdir()
+        r = subprocess.run([str(exe), "bench", str(tns), "-a", "csf", "-i", "1", "-r", "8", "-t", "2",
+                            "-w"], capture_output=True, text=True, timeout=300, cwd=wd, env=env)
+        assert r.returncode == 0, r.stderr
+        assert "** CSF **" in r.stdout
+        outs[tag] = [np.loadtxt(wd / f"csf_mode{m + 1}.mat") for m in range(len(z["dims"]))]
+    for m, (a, b) in enumerate(zip(outs["cpu"], outs["gpu"])):
+        assert a.shape == b.shape == (int(z["dims"][m]), 8)
+        # the dump keeps 9 significant digits
+        assert np.allclose(a, b, rtol=1e-7, atol=1e-7), m

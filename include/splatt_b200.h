@@ -317,6 +317,11 @@ int splatt_b200_level_orders(
 void splatt_b200_shard_range(
     uint64_t nnz, int rank, int count_shards, uint64_t * first, uint64_t * count);
 
+/* Host logic, no GPU needed: expand one CSF (any tiling) to coordinates in storage order --
+ * the first step of mirroring a reference CSF to the device.  ind[m] (nnz uint32 each) and
+ * vals (nnz doubles) are caller-allocated. */
+int splatt_b200_csf_to_coo(splatt_csf const * csf, uint32_t ** ind, double * vals);
+
 /* Enqueue one MTTKRP on `stream` (a cudaStream_t passed as void*; NULL =
  * default stream).  d_mats[m] are DEVICE pointers, row-major with leading
  * dimension ldm (>= ncolumns, even so rows are 16-byte aligned); d_mats[mode]

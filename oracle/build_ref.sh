@@ -90,5 +90,25 @@ if [ -f "$B200LIB" ]; then
   gcc -fopenmp -o "$OUT/splatt_gpu" "${cmdobjs[@]}" "${gpuobjs[@]}" "$B200LIB" \
       "$BLASLIB" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -Wl,-rpath,'$ORIGIN/../../splatt_b200' -lm -lrt
 fi
+# The reference's OWN MTTKRP unit tests (tests/mttkrp_test.c: every fixture x every mode x
+# ONEMODE/TWOMODE/ALLMODE x NOTILE/DENSETILE levels, gold = mttkrp_stream, abs tol 1e-10),
+# built twice: against the reference's kernels (reftest_mttkrp_cpu) and against
+# libsplatt_b200.so through the same symbol rename (reftest_mttkrp_gpu).  The fixture
+# directory is a fixed scratch path that tests/test_reference_unit_tests.py fills from
+# tests/golden/*.npz before running the binaries.
+FIX='"/tmp/splatt_b200_fixtures/"'
+tobjs=()
+for f in main.c mttkrp_test.c; do
+  o="$OUT/obj/t_${f%.c}.o"
+  gcc $CFLAGS -I"$REF/src" -DSPLATT_TEST_DATASETS="$FIX" -DSPLATT_TEST_GRAPHS="$FIX" \
+      -c "$REF/tests/$f" -o "$o"
+  tobjs+=("$o")
+done
+gcc -fopenmp -o "$OUT/reftest_mttkrp_cpu" "${tobjs[@]}" "${objs[@]}" \
+    "$BLASLIB" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -lm -lrt
+if [ -f "$B200LIB" ]; then
+  gcc -fopenmp -o "$OUT/reftest_mttkrp_gpu" "${tobjs[@]}" "${gpuobjs[@]}" "$B200LIB" \
+      "$BLASLIB" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -Wl,-rpath,'$ORIGIN/../../splatt_b200' -lm -lrt
+fi
 rm -rf "$OUT/obj"
 echo "build_ref: built $OUT/libsplatt_ref.so and $OUT/splatt"

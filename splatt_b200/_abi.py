@@ -93,7 +93,7 @@ EXPORTS = [
     "splatt_b200_csf_free", "splatt_b200_mttkrp", "splatt_b200_launch_count",
     "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast", "splatt_b200_gather_probe", "splatt_b200_mttkrp_columns",
     "splatt_b200_als_tail_create", "splatt_b200_als_tail_free", "splatt_b200_als_tail_gram",
-    "splatt_b200_als_tail_update", "splatt_b200_als_tail_fit",
+    "splatt_b200_als_tail_update", "splatt_b200_als_tail_fit", "splatt_b200_csf_to_coo",
 ]
 
 _lib = None
@@ -173,6 +173,8 @@ def load() -> C.CDLL:
     lib.splatt_b200_als_tail_fit.restype = C.c_int
     lib.splatt_b200_als_tail_fit.argtypes = [C.c_void_p, val_p, val_p, C.c_uint64, C.c_double,
                                              C.POINTER(C.c_double), val_p]
+    lib.splatt_b200_csf_to_coo.restype = C.c_int
+    lib.splatt_b200_csf_to_coo.argtypes = [csf_p, u32pp, val_p]
     lib.splatt_b200_gather_probe.restype = C.c_int
     lib.splatt_b200_gather_probe.argtypes = [val_p, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                              C.c_uint64, val_p, C.c_void_p]

@@ -106,49 +106,64 @@ int upload_coo(int N, uint64_t nnz, const uint32_t * const * ind, const double *
 // Walks the tree exactly as the reference's kernels do: children of node f at
 // level l are fptr[l][f]..fptr[l][f+1] (include/splatt/structs.h:51-68); the
 // root id is f itself when fids[0] == NULL (src/csf.c:303-309).
+// One big tile (untiled CSF): loops are parallel inside the tile.  Many tiles
+// (SPLATT_DENSETILE builds up to nthreads^nmodes of them, most tiny or empty):
+// tiles are expanded concurrently, each one serially.
+template <bool PAR>
+void expand_tile(const splatt_csf * ct, const csf_sparsity * pt, uint64_t off, uint32_t ** ind,
+                 double * vals) {
+  const int N = (int)ct->nmodes;
+  const uint64_t tn = pt->nfibs[N - 1];
+  memcpy(vals + off, pt->vals, tn * sizeof(double));
+  {
+    uint32_t * dst = ind[ct->dim_perm[N - 1]] + off;
+    const splatt_idx_t * src = pt->fids[N - 1];
+#pragma omp parallel for schedule(static) if (PAR)
+    for (int64_t n = 0; n < (int64_t)tn; ++n) dst[n] = (uint32_t)src[n];
+  }
+  // leaf-range start of every node, level by level from the bottom
+  std::vector<uint64_t> ls_child, ls;
+  for (int l = N - 2; l >= 0; --l) {
+    const uint64_t nf = pt->nfibs[l];
+    const splatt_idx_t * fp = pt->fptr[l];
+    ls.resize(nf + 1);
+    if (l == N - 2) {
+#pragma omp parallel for schedule(static) if (PAR)
+      for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = fp[f];
+    } else {
+#pragma omp parallel for schedule(static) if (PAR)
+      for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = ls_child[fp[f]];
+    }
+    uint32_t * dst = ind[ct->dim_perm[l]] + off;
+    const splatt_idx_t * ids = pt->fids[l];
+#pragma omp parallel for schedule(dynamic, 256) if (PAR)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+      const uint32_t id = ids ? (uint32_t)ids[f] : (uint32_t)f;
+      for (uint64_t n = ls[f]; n < ls[f + 1]; ++n) dst[n] = id;
+    }
+    ls_child.swap(ls);
+  }
+}
+
 int csf_to_coo(const splatt_csf * ct, std::vector<uint32_t> * ind, std::vector<double> * vals) {
   const int N = (int)ct->nmodes;
   const uint64_t nnz = ct->nnz;
-  for (int m = 0; m < N; ++m) ind[m].assign(nnz, 0u);
+  uint32_t * ip[SPB200_MAXN] = {nullptr};
+  for (int m = 0; m < N; ++m) { ind[m].assign(nnz, 0u); ip[m] = ind[m].data(); }
   vals->assign(nnz, 0.0);
-  uint64_t off = 0;
-  for (uint64_t t = 0; t < ct->ntiles; ++t) {
-    const csf_sparsity * pt = ct->pt + t;
-    if (pt->vals == nullptr) continue;   // empty tile (src/mttkrp.c:682-685)
-    const uint64_t tn = pt->nfibs[N - 1];
-    if (off + tn > nnz) return SPLATT_ERROR_BADINPUT;
-    memcpy(vals->data() + off, pt->vals, tn * sizeof(double));
-    {
-      uint32_t * dst = ind[ct->dim_perm[N - 1]].data() + off;
-      const splatt_idx_t * src = pt->fids[N - 1];
-#pragma omp parallel for schedule(static)
-      for (int64_t n = 0; n < (int64_t)tn; ++n) dst[n] = (uint32_t)src[n];
-    }
-    // leaf-range start of every node, level by level from the bottom
-    std::vector<uint64_t> ls_child, ls;
-    for (int l = N - 2; l >= 0; --l) {
-      const uint64_t nf = pt->nfibs[l];
-      const splatt_idx_t * fp = pt->fptr[l];
-      ls.resize(nf + 1);
-      if (l == N - 2) {
-#pragma omp parallel for schedule(static)
-        for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = fp[f];
-      } else {
-#pragma omp parallel for schedule(static)
-        for (int64_t f = 0; f <= (int64_t)nf; ++f) ls[f] = ls_child[fp[f]];
-      }
-      uint32_t * dst = ind[ct->dim_perm[l]].data() + off;
-      const splatt_idx_t * ids = pt->fids[l];
-#pragma omp parallel for schedule(dynamic, 256)
-      for (int64_t f = 0; f < (int64_t)nf; ++f) {
-        const uint32_t id = ids ? (uint32_t)ids[f] : (uint32_t)f;
-        for (uint64_t n = ls[f]; n < ls[f + 1]; ++n) dst[n] = id;
-      }
-      ls_child.swap(ls);
-    }
-    off += tn;
+  // storage offset of every tile (empty tiles have vals == NULL, src/mttkrp.c:682-685)
+  std::vector<uint64_t> off(ct->ntiles + 1, 0);
+  for (uint64_t t = 0; t < ct->ntiles; ++t)
+    off[t + 1] = off[t] + (ct->pt[t].vals ? ct->pt[t].nfibs[N - 1] : 0);
+  if (off[ct->ntiles] != nnz) return SPLATT_ERROR_BADINPUT;
+  if (ct->ntiles == 1) {
+    if (ct->pt[0].vals) expand_tile<true>(ct, ct->pt, 0, ip, vals->data());
+  } else {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t t = 0; t < (int64_t)ct->ntiles; ++t)
+      if (ct->pt[t].vals) expand_tile<false>(ct, ct->pt + t, off[t], ip, vals->data());
   }
-  return (off == nnz) ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+  return SPLATT_SUCCESS;
 }
 
 int use_device(int device, int * prev) {
@@ -524,6 +539,18 @@ int splatt_b200_level_orders(uint64_t const * dims, int nmodes, int csf_alloc, i
       for (int l = 0; l < SPB200_MAXN; ++l) perms[c * SPB200_MAXN + l] = l < nmodes ? p[c][l] : 0;
   if (mode_csf_map) spb200_mode_csf_map(nmodes, csf_alloc, p[0], mode_csf_map);
   return nc;
+}
+
+int splatt_b200_csf_to_coo(splatt_csf const * csf, uint32_t ** ind, double * vals) {
+  if (!csf || !ind || !vals) return SPLATT_ERROR_BADINPUT;
+  const int N = (int)csf->nmodes;
+  std::vector<uint32_t> iv[SPB200_MAXN];
+  std::vector<double> vv;
+  const int rc = csf_to_coo(csf, iv, &vv);
+  if (rc != SPLATT_SUCCESS) return rc;
+  for (int m = 0; m < N; ++m) memcpy(ind[m], iv[m].data(), csf->nnz * sizeof(uint32_t));
+  memcpy(vals, vv.data(), csf->nnz * sizeof(double));
+  return SPLATT_SUCCESS;
 }
 
 void splatt_b200_shard_range(uint64_t nnz, int rank, int count_shards, uint64_t * first,

@@ -53,3 +53,32 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(A, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(RuntimeError, match="no fallback"):
         A.load()
+
+
+@pytest.mark.parametrize("spec", [((30, 20, 40), 3000), ((12, 10, 14, 8), 2500), ((9, 8, 7, 6, 5), 2000)])
+@pytest.mark.parametrize("tile", [(0, 0), (1, 1), (1, 2), (1, 8)])
+@pytest.mark.parametrize("alloc", [0, 2])
+def test_csf_to_coo_expands_reference_csfs(lib, refmod, spec, tile, alloc):
+    """Host side of the device mirror: a reference CSF (untiled, or DENSETILE at any depth,
+    built with 7 threads like tests/mttkrp_test.c -- up to 7^nmodes mostly empty tiles) expands
+    to exactly the tensor's nonzeros."""
+    import time
+    from tests.util import random_coo
+    dims, inds, vals = random_coo(spec[0], spec[1], seed=4)
+    o = refmod.default_opts()
+    o[0], o[6], o[7], o[8] = 7, alloc, tile[0], tile[1]
+    tt = refmod.RefTensor.from_coo(dims, inds, vals)
+    rc = refmod.RefCsf(tt, o)
+    n = len(vals)
+    for c in range(rc.count):
+        out = [np.zeros(n, dtype=np.uint32) for _ in dims]
+        ov = np.zeros(n)
+        ip = (C.POINTER(C.c_uint32) * len(dims))(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in out])
+        t0 = time.time()
+        import ctypes as _C
+        csf_c = _C.cast(_C.addressof(rc.ptr[c]), _C.POINTER(A.SplattCsf))
+        assert lib.splatt_b200_csf_to_coo(csf_c, ip, ov.ctypes.data_as(A.val_p)) == A.SPLATT_SUCCESS
+        assert time.time() - t0 < 5.0
+        got = sorted(zip(*[a.tolist() for a in out], ov.tolist()))
+        want = sorted(zip(*[i.tolist() for i in inds], vals.tolist()))
+        assert got == want

@@ -70,7 +70,7 @@ def test_zero_index_fixture_equals_one_index_fixture():
         assert np.array_equal(a, b)
 
 
-SPECS = [((13, 7, 11), 150), ((40, 30, 50, 20), 5000), ((12, 15, 10, 20, 9), 3000),
+SPECS = [((30, 50), 700), ((13, 7, 11), 150), ((40, 30, 50, 20), 5000), ((12, 15, 10, 20, 9), 3000),
          ((5, 6, 4, 7, 3, 5), 1500)]
 
 
@@ -102,8 +102,12 @@ def test_restatement_vs_compiled_reference(refmod, spec, alloc):
             assert rel_fro(oc.mttkrp(mats, m), gold[m]) < 1e-12
     for m in range(len(dims)):
         assert rel_fro(restate.mttkrp_coo(dims, inds, vals, mats, m), gold[m]) < 1e-13
-        out, _ = rc.mttkrp_csf(mats, m)          # reference production path == reference gold
-        assert rel_fro(out, gold[m]) < 1e-12
+        if len(dims) > 2:
+            # reference production path == reference gold.  (For matrices the reference's CSF
+            # leaf-mode kernel does not reproduce its own gold -- src/mttkrp.c:860-943 assumes
+            # nmodes >= 3 -- so 2-mode parity is anchored on the COO gold only.)
+            out, _ = rc.mttkrp_csf(mats, m)
+            assert rel_fro(out, gold[m]) < 1e-12
 
 
 def test_restatement_cpd_vs_compiled_reference(refmod):

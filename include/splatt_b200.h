@@ -370,6 +370,68 @@ int splatt_b200_mttkrp_multicast(
     double * mc_out,
     void * stream);
 
+/* The same with the group barrier folded into the kernel's tail (no separate barrier
+ * launch): `sync->mc_flag` is the multicast address and `sync->local_flag` this GPU's own
+ * address of one uint32 in the group's symmetric memory (zero before first use);
+ * `sync->target` = (number of barrier launches so far, including this one) x group size --
+ * the caller counts.  When the kernel completes on a GPU, every peer's reductions have
+ * landed in that GPU's buffer.  All GPUs of the group must launch (an empty shard too). */
+typedef struct
+{
+  uint32_t * mc_flag;
+  uint32_t * local_flag;
+  uint32_t   target;
+  uint32_t   reserved;
+} splatt_b200_group_sync;
+int splatt_b200_mttkrp_multicast_sync(
+    splatt_b200_tensor const * t,
+    int mode,
+    int ncolumns,
+    int ldm,
+    double const * const * d_mats,
+    double * mc_out,
+    splatt_b200_group_sync const * sync,
+    void * stream);
+
+/* Cut shard `rank` of `count` out of a WHOLE device tensor (built with shard_count <= 1)
+ * onto CUDA device `device` (-1 = the whole tensor's device): the same equal-nnz chunk
+ * range splatt_b200_shard_range names, copied device-to-device (P2P) instead of being
+ * re-sorted on every GPU.  Used by the single-process multi-GPU engine. */
+int splatt_b200_tensor_shard(
+    splatt_b200_tensor const * whole, int rank, int count, int device,
+    splatt_b200_tensor ** out);
+
+/* ---- Single-process multi-GPU engine (multi.cu) ------------------------------------
+ * One host process drives `ndevices` GPUs of one NVSwitch box: the reference's
+ * distributed driver for one node (mpi_cpd_als_iterate, src/mpi/mpi_cpd.c:627-804; the
+ * per-mode reduction :250-308) behind the unchanged C API.  The drop-in symbols use it
+ * when the environment says so:
+ *     SPLATT_B200_NGPUS=k            devices 0..k-1
+ *     SPLATT_B200_DEVICES=0,2,5      an explicit list
+ * (splatt_cpd_als, splatt_mttkrp_alloc_ws/_csf and splatt_mttkrp then run on all of
+ * them).  The tensor is built once on the first device, cut into equal-nnz shares that
+ * move device-to-device; the per-mode sum over devices happens inside the MTTKRP kernel
+ * through an NVLink multicast mapping (CUDA driver multicast objects) with the group
+ * barrier in the kernel's tail; without multicast support a peer-memory reduce kernel
+ * ordered by CUDA events takes over (SPLATT_B200_MULTICAST=0 forces that path). */
+typedef struct splatt_b200_multi splatt_b200_multi;
+int  splatt_b200_multi_env_devices(int * devices, int cap);   /* parsed env, 0 = single GPU */
+int  splatt_b200_multi_create(splatt_csf const * tensors, int csf_alloc, int ncolumns,
+                              int const * devices, int ndevices, int verbosity,
+                              splatt_b200_multi ** out);
+void splatt_b200_multi_free(splatt_b200_multi * h);
+int  splatt_b200_multi_info(splatt_b200_multi const * h, int * ndevices, int * multicast,
+                            uint64_t * nnz_local, uint64_t * device_bytes);
+/* MTTKRP of `mode` with HOST matrices (row-major dims[m] x ncolumns; mats[mode] ignored):
+ * factors go to every device, result comes back as one row slice per device. */
+int  splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode,
+                                   double const * const * mats, double * out_host);
+/* CPD-ALS over all devices; same contract as splatt_cpd_als (`tensors` only supplies the
+ * Frobenius norm for the fit). */
+int  splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
+                               double const * options, splatt_kruskal * factored);
+double splatt_b200_multi_last_ms(splatt_b200_multi const * h);
+
 /* The dense tail of one ALS mode update on the device -- the kernels splatt_cpd_als uses --
  * as separate entry points, so a multi-GPU driver can interleave them with its exchange:
  *   local MTTKRP (shard) -> sum over ranks -> splatt_b200_als_tail_update (replicated).
@@ -396,6 +458,16 @@ int  splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_fa
 int splatt_b200_gather_probe(
     double const * d_mat, int ncolumns, int ldm,
     uint32_t const * d_idx, uint64_t nidx, double * d_sink, void * stream);
+
+/* The same probe at a chosen shape: `ctas_per_sm` (1..8) CTAs of 256 threads resident per
+ * SM, `rows_in_flight` (2/4/8/16) independent row loads per lane group, `no_allocate` != 0
+ * loads with ld.global.nc.L1::no_allocate, `smem_bytes` of dynamic shared memory reserved
+ * per CTA (shrinks the L1).  ncolumns must be 16, 32 or 64.
+ * scripts/probe_sweep.py sweeps the shapes; the best point is the access pattern's ceiling. */
+int splatt_b200_gather_probe_ex(
+    double const * d_mat, int ncolumns, int ldm,
+    uint32_t const * d_idx, uint64_t nidx, double * d_sink,
+    int ctas_per_sm, int rows_in_flight, int no_allocate, int smem_bytes, void * stream);
 
 /* Number of kernels the engine has launched in this process (bench.py's
  * gpu_launches evidence). */

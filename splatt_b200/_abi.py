@@ -82,6 +82,11 @@ class BuildOpts(C.Structure):
                 ("reserved", C.c_int32 * 9)]
 
 
+class GroupSync(C.Structure):
+    _fields_ = [("mc_flag", C.c_void_p), ("local_flag", C.c_void_p), ("target", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 LIB_PATH = Path(__file__).resolve().parent / "libsplatt_b200.so"
 
 # every symbol include/splatt_b200.h declares
@@ -91,9 +96,13 @@ EXPORTS = [
     "splatt_b200_tensor_from_csf", "splatt_b200_tensor_from_coo", "splatt_b200_tensor_free",
     "splatt_b200_tensor_info", "splatt_b200_mode_info", "splatt_b200_csf_alloc",
     "splatt_b200_csf_free", "splatt_b200_mttkrp", "splatt_b200_launch_count",
-    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast", "splatt_b200_gather_probe", "splatt_b200_mttkrp_columns",
+    "splatt_b200_version", "splatt_b200_level_orders", "splatt_b200_shard_range", "splatt_b200_mttkrp_multicast", "splatt_b200_gather_probe", "splatt_b200_gather_probe_ex", "splatt_b200_mttkrp_columns",
     "splatt_b200_als_tail_create", "splatt_b200_als_tail_free", "splatt_b200_als_tail_gram",
     "splatt_b200_als_tail_update", "splatt_b200_als_tail_fit", "splatt_b200_csf_to_coo",
+    "splatt_b200_tensor_shard", "splatt_b200_mttkrp_multicast_sync",
+    "splatt_b200_multi_env_devices", "splatt_b200_multi_create", "splatt_b200_multi_free",
+    "splatt_b200_multi_info", "splatt_b200_multi_mttkrp_host", "splatt_b200_multi_cpd_als",
+    "splatt_b200_multi_last_ms",
 ]
 
 _lib = None
@@ -178,6 +187,33 @@ def load() -> C.CDLL:
     lib.splatt_b200_gather_probe.restype = C.c_int
     lib.splatt_b200_gather_probe.argtypes = [val_p, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                              C.c_uint64, val_p, C.c_void_p]
+    lib.splatt_b200_gather_probe_ex.restype = C.c_int
+    lib.splatt_b200_gather_probe_ex.argtypes = [val_p, C.c_int, C.c_int, C.POINTER(C.c_uint32),
+                                                C.c_uint64, val_p, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p]
+    lib.splatt_b200_tensor_shard.restype = C.c_int
+    lib.splatt_b200_tensor_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.POINTER(C.c_void_p)]
+    lib.splatt_b200_mttkrp_multicast_sync.restype = C.c_int
+    lib.splatt_b200_mttkrp_multicast_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp,
+                                                      val_p, C.POINTER(GroupSync), C.c_void_p]
+    lib.splatt_b200_multi_env_devices.restype = C.c_int
+    lib.splatt_b200_multi_env_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+    lib.splatt_b200_multi_create.restype = C.c_int
+    lib.splatt_b200_multi_create.argtypes = [csf_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                             C.c_int, C.POINTER(C.c_void_p)]
+    lib.splatt_b200_multi_free.restype = None
+    lib.splatt_b200_multi_free.argtypes = [C.c_void_p]
+    lib.splatt_b200_multi_info.restype = C.c_int
+    lib.splatt_b200_multi_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           idx_p, idx_p]
+    lib.splatt_b200_multi_mttkrp_host.restype = C.c_int
+    lib.splatt_b200_multi_mttkrp_host.argtypes = [C.c_void_p, C.c_int, vpp, val_p]
+    lib.splatt_b200_multi_cpd_als.restype = C.c_int
+    lib.splatt_b200_multi_cpd_als.argtypes = [C.c_void_p, csf_p, C.POINTER(C.c_double),
+                                              C.POINTER(SplattKruskal)]
+    lib.splatt_b200_multi_last_ms.restype = C.c_double
+    lib.splatt_b200_multi_last_ms.argtypes = [C.c_void_p]
     lib.splatt_b200_launch_count.restype = C.c_uint64
     lib.splatt_b200_launch_count.argtypes = []
     lib.splatt_b200_version.restype = C.c_char_p

@@ -313,6 +313,15 @@ class Tensor:
         _check(rc, "splatt_b200_mttkrp")
         return out
 
+    def shard(self, rank: int, count: int, device: int = -1) -> "Tensor":
+        """Cut shard `rank` of `count` out of this (whole) tensor onto `device`
+        (splatt_b200_tensor_shard): the equal-nnz chunk range of every stream, copied
+        device to device instead of being rebuilt."""
+        out = C.c_void_p()
+        _check(self.lib.splatt_b200_tensor_shard(self.h, rank, count, device, C.byref(out)),
+               "splatt_b200_tensor_shard")
+        return Tensor(out, self.lib)
+
     def free(self):
         if self.h:
             self.lib.splatt_b200_tensor_free(self.h)
@@ -327,3 +336,67 @@ class Tensor:
 
 def launch_count() -> int:
     return int(A.load().splatt_b200_launch_count())
+
+
+class MultiGpu:
+    """Single-process multi-GPU engine (splatt_b200_multi): one host process, several
+    devices, the exchange fused into the MTTKRP kernel over NVLink multicast (or the
+    peer-memory reduce where there is no multicast)."""
+
+    def __init__(self, csf_ptr, csf_alloc: int, ncolumns: int, devices: Sequence[int],
+                 verbosity: int = 0):
+        self.lib = A.load()
+        self.csf_ptr = csf_ptr
+        self.ncolumns = ncolumns
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        _check(self.lib.splatt_b200_multi_create(csf_ptr, csf_alloc, ncolumns, devs, len(devices),
+                                                 verbosity, C.byref(self.h)),
+               "splatt_b200_multi_create")
+        self.nmodes = int(csf_ptr[0].nmodes)
+        self.dims = [int(csf_ptr[0].dims[m]) for m in range(self.nmodes)]
+        nd, mc = C.c_int(), C.c_int()
+        nl = (A.idx_t * 16)()
+        db = (A.idx_t * 16)()
+        _check(self.lib.splatt_b200_multi_info(self.h, C.byref(nd), C.byref(mc), nl, db),
+               "splatt_b200_multi_info")
+        self.ndevices = nd.value
+        self.multicast = bool(mc.value)
+        self.nnz_local = [int(nl[i]) for i in range(self.ndevices)]
+        self.device_bytes = [int(db[i]) for i in range(self.ndevices)]
+
+    def mttkrp_host(self, mode: int, mats: Sequence[Optional[np.ndarray]],
+                    out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.dims[mode], self.ncolumns), dtype=np.float64)
+        keep, arr = _mat_ptrs([None if m == mode else mats[m] for m in range(self.nmodes)])
+        _check(self.lib.splatt_b200_multi_mttkrp_host(self.h, mode, arr, _dptr(out)),
+               "splatt_b200_multi_mttkrp_host")
+        return out
+
+    def cpd_als(self, opts: np.ndarray, seed: Optional[int] = None):
+        if seed is not None:
+            C.CDLL(None).srand(C.c_uint(seed))
+        k = A.SplattKruskal()
+        o = np.ascontiguousarray(opts, dtype=np.float64)
+        _check(self.lib.splatt_b200_multi_cpd_als(self.h, self.csf_ptr, _dptr(o), C.byref(k)),
+               "splatt_b200_multi_cpd_als")
+        n = int(k.nmodes)
+        R = self.ncolumns
+        lam = np.ctypeslib.as_array(k.lambda_, shape=(R,)).copy()
+        facs = [np.ctypeslib.as_array(k.factors[m], shape=(int(k.dims[m]), R)).copy()
+                for m in range(n)]
+        fit = float(k.fit)
+        self.lib.splatt_free_kruskal(C.byref(k))
+        return fit, lam, facs
+
+    def free(self):
+        if self.h:
+            self.lib.splatt_b200_multi_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -17,6 +17,9 @@
 //                      counting, never by pointer chasing.
 //   up[l][f]   uint32 index (mode perm[l]) of node f at level l, l = 0..N-3
 //                (the reference's fids[l], always materialised for l = 0).
+//   anc[n]     (N >= 4 only) uint32 index (mode perm[N-3]) of record n's level-(N-3)
+//                ancestor: the root kernel gathers that row whenever c >= 2 without
+//                first fetching an id from up[N-3] (no dependent load chain).
 //   desc[c][l] for every chunk of SPB200_CHUNK records, the node number at
 //                level l (l = 0..N-3) that contains the chunk's first record,
 //                so any chunk boundary is a legal place to start a traversal.
@@ -52,6 +55,7 @@ struct FiberStream {
   uint64_t nnodes[SPB200_MAXN] = {0};     // nodes per level (of the records held)
   SpRec *    rec = nullptr;
   uint32_t * up[SPB200_MAXN] = {nullptr}; // levels 0..N-3 (of the records held)
+  uint32_t * anc = nullptr;                // N >= 4: level-(N-3) index of every record (padded to 16 B)
   uint32_t * desc = nullptr;               // local chunks x (N-2)
   uint64_t nchunks = 0;                    // local chunks
   size_t   bytes = 0;                      // HBM held
@@ -88,6 +92,7 @@ struct splatt_b200_tensor {
   int      shard_rank = 0, shard_count = 1;
   std::vector<FiberStream> streams;
   ModePlan plan[SPB200_MAXN];
+  uint32_t * cta_done = nullptr;   // scratch of the in-kernel group barrier (lazily allocated)
 };
 
 // Kernel argument block (passed by value).
@@ -95,6 +100,7 @@ struct MttkrpArgs {
   const SpRec *    rec;
   const uint32_t * up[SPB200_MAXN - 2];
   const uint32_t * desc;
+  const uint32_t * anc;                 // N >= 4 root kernels: level-(N-3) index per record
   const double *   mats[SPB200_MAXN];   // by LEVEL: factor of mode perm[l]
   double *         out;
   unsigned long long nrec;
@@ -105,6 +111,23 @@ struct MttkrpArgs {
   int              outdepth;  // level of the output mode
   int              ktiled;    // stream is leaf-tile ordered: keep non-leaf gathers out of L1
   int              multicast; // `out` is an NVLink multicast address: reduce with multimem.red
+  // Group barrier folded into the kernel's tail (multicast launches only; null = off):
+  // after its last row reduction every CTA fences at system scope; the last CTA to finish
+  // adds 1 to the group's flag on EVERY GPU (multimem.red on sync_mc) and spins on this
+  // GPU's copy until it reaches sync_target (= launches so far x group size).  When the
+  // kernel exits, every peer's reductions have landed in this GPU's output buffer.
+  uint32_t *       sync_mc;
+  uint32_t *       sync_local;
+  uint32_t *       sync_cta;   // this GPU's finished-CTA counter (device memory, starts at 0)
+  uint32_t         sync_target;
+};
+
+// Host-side description of the group barrier (see MttkrpArgs).
+struct GroupSync {
+  uint32_t * mc_flag = nullptr;
+  uint32_t * local_flag = nullptr;
+  uint32_t * cta_done = nullptr;
+  uint32_t   target = 0;
 };
 
 #define SPB200_CUDA_OK(call)                                                   \
@@ -130,6 +153,11 @@ int spb200_build_stream(int nmodes, const uint64_t * dims, uint64_t nnz,
                         int shard_rank, int shard_count,
                         const StreamTiling & tiling, FiberStream * out);
 void spb200_free_stream(FiberStream * s);
+// Cut the chunk range [c0, c1) out of a WHOLE (unsharded, untiled) stream living on device
+// `src_dev` into a stand-alone stream on device `dst_dev` (node numbers re-based): what a
+// shard built by spb200_build_stream(shard_rank, shard_count) holds, without re-sorting.
+int spb200_slice_stream(const FiberStream & whole, int src_dev, uint64_t c0, uint64_t c1,
+                        int dst_dev, FiberStream * out);
 
 // Host CSF arrays from device COO (for splatt_b200_csf_alloc).
 int spb200_build_host_csf(int nmodes, const uint64_t * dims, uint64_t nnz,
@@ -141,8 +169,9 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
                          int ncolumns, int ldm,
                          const double * const * d_mats_by_mode, double * d_out,
                          uint64_t out_rows, cudaStream_t stream, bool multicast_out = false,
-                         int col_begin = 0, int col_count = 0);
+                         int col_begin = 0, int col_count = 0, const GroupSync * sync = nullptr);
 extern unsigned long long g_spb200_launches;
+inline void spb200_count_launches(unsigned n) { __atomic_fetch_add(&g_spb200_launches, n, __ATOMIC_RELAXED); }
 
 // mttkrp_tiled.cu -- 3-mode root kernel with the leaf factor staged tile by tile in smem
 bool spb200_tiled_applicable(const FiberStream & s, int kind, int ncolumns, int ldm);

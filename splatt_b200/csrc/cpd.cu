@@ -233,6 +233,22 @@ double csf_frobsq(const splatt_csf * t) {   // reference: src/csf.c:817-851
 }
 
 
+}  // namespace
+
+// shared with the multi-GPU driver (multi.cu)
+double spb200_cpd_rand_val() { return rand_val(); }
+double spb200_csf_frobsq(const splatt_csf * t) { return csf_frobsq(t); }
+// post-process (src/cpd.c:391-411): 2-normalise every factor into lambda
+void spb200_cpd_postprocess(double ** mats, const uint64_t * dims, int N, int R, double * lambda) {
+  std::vector<double> tmp(R);
+  for (int m = 0; m < N; ++m) {
+    normalize_cols(mats[m], dims[m], R, tmp.data(), true);
+    for (int f = 0; f < R; ++f) lambda[f] *= tmp[f];
+  }
+}
+
+namespace {
+
 // ---------------------------------------------------------------------------
 // Device-side ALS tail: the same five steps as the host
 // functions above, as small kernels on the MTTKRP stream, so that an iteration
@@ -496,7 +512,7 @@ struct DevTail {
     cudaMemsetAsync(G, 0, sizeof(double) * R * R, s);
     const unsigned blocks = (unsigned)std::min<uint64_t>((I + 31) / 32, 592);
     k_gram<<<blocks, 256, 32 * R * 8, s>>>(A, I, R, ld, G);
-    g_spb200_launches += 1;
+    spb200_count_launches(1);
   }
   // one mode step after the MTTKRP: d_out (M1) -> d_mat (new factor), lambda, Gram
   void mode_step(const double * d_out, double * d_mat, uint64_t I, int m, bool two_norm) {
@@ -508,7 +524,7 @@ struct DevTail {
     k_colnorm<<<g, 256, 0, s>>>(d_mat, I, R, ld, two_norm ? 1 : 0, lam_acc);
     k_finish_lambda<<<(R + 127) / 128, 128, 0, s>>>(lam_acc, R, two_norm ? 1 : 0, lambda);
     k_scale_cols<<<(unsigned)((I * R + 255) / 256), 256, 0, s>>>(d_mat, I, R, ld, lambda);
-    g_spb200_launches += 5;
+    spb200_count_launches(5);
     gram(d_mat, I, m);
   }
 };
@@ -527,6 +543,20 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
   const int R = (int)nfactors;
   const int ldm = R + (R & 1);
   const int verbosity = (int)options[SPLATT_OPTION_VERBOSITY];
+  {
+    // SPLATT_B200_NGPUS=k / SPLATT_B200_DEVICES=a,b,..: one process, k devices (multi.cu)
+    int devs[16];
+    const int nd = splatt_b200_multi_env_devices(devs, 16);
+    if (nd > 1) {
+      splatt_b200_multi * mh = nullptr;
+      int mrc = splatt_b200_multi_create(tensors, (int)options[SPLATT_OPTION_CSF_ALLOC], R, devs, nd,
+                                         verbosity, &mh);
+      if (mrc != SPLATT_SUCCESS) return mrc;
+      mrc = splatt_b200_multi_cpd_als(mh, tensors, options, factored);
+      splatt_b200_multi_free(mh);
+      return mrc;
+    }
+  }
   uint64_t dims[SPB200_MAXN], maxdim = 0;
   for (int m = 0; m < N; ++m) { dims[m] = tensors[0].dims[m]; maxdim = std::max(maxdim, dims[m]); }
   // Where the dense ALS tail runs.  Default: on the device.
@@ -644,7 +674,7 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
       cudaMemsetAsync(tail.inner, 0, sizeof(double), stream);
       k_inner<<<296, 256, 0, stream>>>(d_mats[N - 1], d_out, dims[N - 1], R, ldm, tail.lambda,
                                        tail.inner);
-      g_spb200_launches += 1;
+      spb200_count_launches(1);
       cudaMemcpyAsync(tail.h_back, tail.ata, nb * 8, cudaMemcpyDeviceToHost, stream);
       cudaMemcpyAsync(tail.h_back + nb, tail.lambda, R * 8, cudaMemcpyDeviceToHost, stream);
       cudaMemcpyAsync(tail.h_back + nb + R, tail.inner, 8, cudaMemcpyDeviceToHost, stream);
@@ -667,13 +697,7 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
     ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
   }
   // post-process (src/cpd.c:391-411): 2-normalise every factor into lambda
-  if (ok) {
-    std::vector<double> tmp(R);
-    for (int m = 0; m < N; ++m) {
-      normalize_cols(mats[m], dims[m], R, tmp.data(), true);
-      for (int f = 0; f < R; ++f) lambda[f] *= tmp[f];
-    }
-  }
+  if (ok) spb200_cpd_postprocess(mats, dims, N, R, lambda);
   if (stream) cudaStreamSynchronize(stream);
   for (int m = 0; m < N; ++m) if (d_mats[m]) cudaFree(d_mats[m]);
   if (d_out) cudaFree(d_out);
@@ -752,7 +776,7 @@ int splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_fac
   const size_t nb = (size_t)N * R * R;
   cudaMemsetAsync(t.inner, 0, sizeof(double), t.s);
   k_inner<<<296, 256, 0, t.s>>>(d_last_factor, d_last_m1, rows, R, t.ld, t.lambda, t.inner);
-  g_spb200_launches += 1;
+  spb200_count_launches(1);
   cudaMemcpyAsync(t.h_back, t.ata, nb * 8, cudaMemcpyDeviceToHost, t.s);
   cudaMemcpyAsync(t.h_back + nb, t.lambda, R * 8, cudaMemcpyDeviceToHost, t.s);
   cudaMemcpyAsync(t.h_back + nb + R, t.inner, 8, cudaMemcpyDeviceToHost, t.s);

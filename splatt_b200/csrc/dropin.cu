@@ -23,6 +23,7 @@ struct WsPriv {
   splatt_mttkrp_ws pub;
   uint64_t magic;
   splatt_b200_tensor * T;
+  splatt_b200_multi * multi;     // several GPUs configured (SPLATT_B200_NGPUS / _DEVICES): multi.cu
   int N;
   uint64_t dims[SPB200_MAXN];
   int ncolumns;
@@ -41,6 +42,13 @@ struct WsPriv {
   bool pin;
   int npinned;
   void * pinned[4 * SPB200_MAXN];
+  size_t pinned_bytes[4 * SPB200_MAXN];
+  // Pageable caller buffers (the reference's splatt_malloc memory): copies are staged through
+  // page-locked bounce buffers owned by the workspace, filled / drained by a few host threads,
+  // so that the PCIe copies stay asynchronous and the column-block pipeline still overlaps.
+  double * stage_in;  size_t stage_in_cap;     // doubles
+  double * stage_out; size_t stage_out_cap;
+  cudaEvent_t ev_d2h[2];
 };
 
 int layout_from_env() {
@@ -53,10 +61,22 @@ int layout_from_env() {
 void pin_once(WsPriv * w, void * p, size_t bytes) {
   if (!w->pin || !p) return;
   for (int i = 0; i < w->npinned; ++i)
-    if (w->pinned[i] == p) return;
+    if (w->pinned[i] == p) {
+      if (w->pinned_bytes[i] >= bytes) return;
+      // the same buffer seen with a larger extent (the reference's CPD driver reuses one
+      // maxdim x J output for every mode, src/cpd.c:322-327): register the larger range
+      cudaHostUnregister(p);
+      if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) w->pinned_bytes[i] = bytes;
+      else { cudaGetLastError(); w->pinned[i] = w->pinned[--w->npinned]; w->pinned_bytes[i] = w->pinned_bytes[w->npinned]; }
+      return;
+    }
   if (w->npinned >= 4 * SPB200_MAXN) return;
-  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) w->pinned[w->npinned++] = p;
-  else cudaGetLastError();   // already pinned / not registrable: copy works either way
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    w->pinned[w->npinned] = p;
+    w->pinned_bytes[w->npinned++] = bytes;
+  } else {
+    cudaGetLastError();   // already pinned / not registrable: copy works either way
+  }
 }
 
 void free_priv(WsPriv * w) {
@@ -70,8 +90,12 @@ void free_priv(WsPriv * w) {
   for (int i = 0; i < 2; ++i) {
     if (w->ev_h2d[i]) cudaEventDestroy(w->ev_h2d[i]);
     if (w->ev_k[i]) cudaEventDestroy(w->ev_k[i]);
+    if (w->ev_d2h[i]) cudaEventDestroy(w->ev_d2h[i]);
   }
+  if (w->stage_in) cudaFreeHost(w->stage_in);
+  if (w->stage_out) cudaFreeHost(w->stage_out);
   if (w->T) splatt_b200_tensor_free(w->T);
+  if (w->multi) splatt_b200_multi_free(w->multi);
   w->magic = 0;
   free(w);
 }
@@ -88,33 +112,98 @@ cudaError_t d2h_matrix(double * dst, const double * src, int ldm, uint64_t I, ui
   return cudaMemcpy2DAsync(dst, J * 8, src, (size_t)ldm * 8, J * 8, I, cudaMemcpyDeviceToHost, s);
 }
 
-bool is_pinned(const void * p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return at.type == cudaMemoryTypeHost;
+bool is_pinned(const void * p, size_t bytes) {
+  // both ends of the range must be page-locked host memory
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a0.type != cudaMemoryTypeHost) return false;
+  if (bytes <= 1) return true;
+  if (cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a1.type == cudaMemoryTypeHost;
 }
 
-// Column-block pipeline (page-locked host buffers only): MTTKRP is independent per column,
-// so the factor columns of block 1 cross PCIe while the kernel runs on block 0, and block 0's
-// result goes back while the kernel runs on block 1.
-//   copy stream :  H2D blk0 | H2D blk1 |        D2H blk0 |          D2H blk1
-//   kernel stream:           kernel blk0        | kernel blk1
-cudaError_t pipelined_call(WsPriv * w, splatt_b200_matrix_t ** mats, int mode, uint64_t J, int * rc) {
+int stage_threads() {
+  static int v = 0;
+  if (v == 0) {
+    const char * e = getenv("SPLATT_B200_STAGE_THREADS");
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+    if (v > 64) v = 64;
+  }
+  return v;
+}
+
+// rows x wcols block of a row-major (ld_src) matrix -> dense rows x wcols, and back
+void pack_cols(double * dst, const double * src, uint64_t rows, size_t ld_src, size_t wcols) {
+#pragma omp parallel for schedule(static) num_threads(stage_threads())
+  for (int64_t i = 0; i < (int64_t)rows; ++i)
+    memcpy(dst + (size_t)i * wcols, src + (size_t)i * ld_src, wcols * sizeof(double));
+}
+void unpack_cols(double * dst, size_t ld_dst, const double * src, uint64_t rows, size_t wcols) {
+#pragma omp parallel for schedule(static) num_threads(stage_threads())
+  for (int64_t i = 0; i < (int64_t)rows; ++i)
+    memcpy(dst + (size_t)i * ld_dst, src + (size_t)i * wcols, wcols * sizeof(double));
+}
+
+bool ensure_stage(WsPriv * w, size_t in_doubles, size_t out_doubles) {
+  if (in_doubles > w->stage_in_cap) {
+    if (w->stage_in) cudaFreeHost(w->stage_in);
+    w->stage_in = nullptr; w->stage_in_cap = 0;
+    if (cudaMallocHost(&w->stage_in, in_doubles * 8) != cudaSuccess) { cudaGetLastError(); return false; }
+    w->stage_in_cap = in_doubles;
+  }
+  if (out_doubles > w->stage_out_cap) {
+    if (w->stage_out) cudaFreeHost(w->stage_out);
+    w->stage_out = nullptr; w->stage_out_cap = 0;
+    if (cudaMallocHost(&w->stage_out, out_doubles * 8) != cudaSuccess) { cudaGetLastError(); return false; }
+    w->stage_out_cap = out_doubles;
+  }
+  return true;
+}
+
+// Column-block pipeline: MTTKRP is independent per column, so the factor columns of block 1
+// cross PCIe while the kernel runs on block 0, and block 0's result goes back while the
+// kernel runs on block 1.
+//   host (staged): pack blk0 | pack blk1 |                      unpack blk0 | unpack blk1
+//   copy stream  :      H2D blk0 | H2D blk1 |        D2H blk0 |          D2H blk1
+//   kernel stream:                kernel blk0        | kernel blk1
+// `staged`: the caller's buffers are pageable -- go through the workspace's page-locked
+// bounce buffers (packed per column block); otherwise DMA straight from/to the caller.
+cudaError_t pipelined_call(WsPriv * w, splatt_b200_matrix_t ** mats, int mode, uint64_t J,
+                           int nblocks, bool staged, int * rc) {
   const int N = w->N;
   const int rpad = w->ldm;
   const int half = ((rpad / 2) + 1) & ~1;                 // even split point
-  const int cb[3] = {0, half, rpad};
+  int cb[3] = {0, half, rpad};
+  if (nblocks == 1) { cb[1] = rpad; cb[2] = rpad; }
+  splatt_b200_matrix_t * M = mats[SPLATT_B200_MAX_NMODES];
+  size_t in_rows = 0;
+  for (int m = 0; m < N; ++m) if (m != mode) in_rows += w->dims[m];
+  if (staged && !ensure_stage(w, in_rows * J, w->dims[mode] * J)) return cudaErrorMemoryAllocation;
   cudaError_t e = cudaSuccess;
-  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+  size_t in_off = 0;
+  for (int b = 0; b < nblocks && e == cudaSuccess; ++b) {
     const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
     for (int m = 0; m < N && e == cudaSuccess && wcols; ++m) {
       if (m == mode) continue;
-      e = cudaMemcpy2DAsync(w->d_mats[m] + c0, (size_t)w->ldm * 8, mats[m]->vals + c0, J * 8,
-                            wcols * 8, w->dims[m], cudaMemcpyHostToDevice, w->copy_stream);
+      const double * src = mats[m]->vals + c0;
+      size_t spitch = J * 8;
+      if (staged) {
+        double * st = w->stage_in + in_off;
+        pack_cols(st, src, w->dims[m], J, wcols);
+        in_off += w->dims[m] * wcols;
+        src = st;
+        spitch = wcols * 8;
+      }
+      e = cudaMemcpy2DAsync(w->d_mats[m] + c0, (size_t)w->ldm * 8, src, spitch, wcols * 8,
+                            w->dims[m], cudaMemcpyHostToDevice, w->copy_stream);
     }
     if (e == cudaSuccess) e = cudaEventRecord(w->ev_h2d[b], w->copy_stream);
   }
-  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+  for (int b = 0; b < nblocks && e == cudaSuccess; ++b) {
     e = cudaStreamWaitEvent(w->stream, w->ev_h2d[b], 0);
     if (e != cudaSuccess) break;
     *rc = splatt_b200_mttkrp_columns(w->T, mode, w->ncolumns, w->ldm, w->d_mats, w->d_out, cb[b],
@@ -122,13 +211,28 @@ cudaError_t pipelined_call(WsPriv * w, splatt_b200_matrix_t ** mats, int mode, u
     if (*rc != SPLATT_SUCCESS) return cudaSuccess;
     e = cudaEventRecord(w->ev_k[b], w->stream);
   }
-  splatt_b200_matrix_t * M = mats[SPLATT_B200_MAX_NMODES];
-  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+  size_t out_off[2] = {0, 0};
+  for (int b = 0; b < nblocks && e == cudaSuccess; ++b) {
     const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
     e = cudaStreamWaitEvent(w->copy_stream, w->ev_k[b], 0);
-    if (e == cudaSuccess && wcols)
-      e = cudaMemcpy2DAsync(M->vals + c0, J * 8, w->d_out + c0, (size_t)w->ldm * 8, wcols * 8,
-                            w->dims[mode], cudaMemcpyDeviceToHost, w->copy_stream);
+    if (b == 1) out_off[1] = w->dims[mode] * (std::min<size_t>(cb[1], J));
+    if (e == cudaSuccess && wcols) {
+      if (staged)
+        e = cudaMemcpy2DAsync(w->stage_out + out_off[b], wcols * 8, w->d_out + c0, (size_t)w->ldm * 8,
+                              wcols * 8, w->dims[mode], cudaMemcpyDeviceToHost, w->copy_stream);
+      else
+        e = cudaMemcpy2DAsync(M->vals + c0, J * 8, w->d_out + c0, (size_t)w->ldm * 8, wcols * 8,
+                              w->dims[mode], cudaMemcpyDeviceToHost, w->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(w->ev_d2h[b], w->copy_stream);
+  }
+  if (staged) {
+    for (int b = 0; b < nblocks && e == cudaSuccess; ++b) {
+      const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+      e = cudaEventSynchronize(w->ev_d2h[b]);
+      if (e == cudaSuccess && wcols)
+        unpack_cols(M->vals + c0, J, w->stage_out + out_off[b], w->dims[mode], wcols);
+    }
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(w->copy_stream);
   return e;
@@ -172,6 +276,21 @@ splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
   w->pub.privatize_buffer = nullptr;
   w->pub.reduction_time = 0.;
 
+  w->ncolumns = (int)ncolumns;
+  w->ldm = (int)(ncolumns + (ncolumns & 1));
+  {
+    int devs[16];
+    const int nd = splatt_b200_multi_env_devices(devs, 16);
+    if (nd > 1) {
+      // one process, several GPUs: shards + fused exchange live in the multi engine
+      if (splatt_b200_multi_create(tensors, csf_alloc, (int)ncolumns, devs, nd,
+                                   (int)opts[SPLATT_OPTION_VERBOSITY], &w->multi) != SPLATT_SUCCESS) {
+        free_priv(w);
+        return nullptr;
+      }
+      return &w->pub;
+    }
+  }
   splatt_b200_build_opts bo;
   memset(&bo, 0, sizeof(bo));
   bo.layout = layout_from_env();
@@ -196,7 +315,8 @@ splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
   ok = ok && cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i)
     ok = cudaEventCreateWithFlags(&w->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&w->ev_k[i], cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&w->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&w->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     fprintf(stderr, "SPLATT: out of device memory for MTTKRP workspace (%s)\n",
             cudaGetErrorString(cudaGetLastError()));
@@ -240,21 +360,37 @@ void splatt_mttkrp_csf(splatt_csf const * const tensors, splatt_b200_matrix_t **
   auto t0 = std::chrono::steady_clock::now();
   cudaError_t e = cudaSuccess;
   int rc = SPLATT_SUCCESS;
-  bool all_pinned = J >= 16;                           // narrow matrices: one block is enough
+  bool all_pinned = true;
   for (int m = 0; m < N; ++m) {
     if (m == (int)mode) continue;                      // never read (may alias the output)
     pin_once(w, mats[m]->vals, w->dims[m] * J * sizeof(double));
-    all_pinned = all_pinned && is_pinned(mats[m]->vals);
+    all_pinned = all_pinned && is_pinned(mats[m]->vals, w->dims[m] * J * sizeof(double));
   }
   pin_once(w, M->vals, w->dims[mode] * J * sizeof(double));
-  all_pinned = all_pinned && is_pinned(M->vals);
-  static int use_pipe = -1;
+  all_pinned = all_pinned && is_pinned(M->vals, w->dims[mode] * J * sizeof(double));
+  if (w->multi) {
+    const double * hm[SPB200_MAXN] = {nullptr};
+    for (int m = 0; m < N; ++m) hm[m] = (m == (int)mode) ? nullptr : mats[m]->vals;
+    if (splatt_b200_multi_mttkrp_host(w->multi, (int)mode, hm, M->vals) != SPLATT_SUCCESS) {
+      fprintf(stderr, "SPLATT: multi-GPU MTTKRP failed\n");
+      abort();
+    }
+    w->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (opts && (int)opts[SPLATT_OPTION_VERBOSITY] == SPLATT_VERBOSITY_MAX)
+      printf("MTTKRP mode %llu: %0.6fs (B200 x N, host buffers)\n", (unsigned long long)mode + 1,
+             w->last_ms * 1e-3);
+    return;
+  }
+  static int use_pipe = -1, use_stage = -1;
   if (use_pipe < 0) {
     const char * pe = getenv("SPLATT_B200_PIPELINE");
     use_pipe = (pe && atoi(pe) == 0) ? 0 : 1;
+    const char * se = getenv("SPLATT_B200_STAGE");
+    use_stage = (se && atoi(se) == 0) ? 0 : 1;
   }
-  if (all_pinned && use_pipe) {
-    e = pipelined_call(w, mats, (int)mode, J, &rc);
+  if (all_pinned || use_stage) {
+    // narrow matrices: one block is enough
+    e = pipelined_call(w, mats, (int)mode, J, (J >= 16 && use_pipe) ? 2 : 1, !all_pinned, &rc);
   } else {
     for (int m = 0; m < N && e == cudaSuccess; ++m) {
       if (m == (int)mode) continue;

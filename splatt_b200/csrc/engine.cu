@@ -68,6 +68,20 @@ void spb200_shard_chunks(uint64_t nnz, int rank, int nshards, uint64_t * c0, uin
 
 namespace {
 
+// Run on the tensor's device, restore the caller's afterwards.
+struct DeviceGuard {
+  int prev = -1, want = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) : want(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != want && cudaSetDevice(want) != cudaSuccess) {
+      fprintf(stderr, "SPLATT: cannot switch to CUDA device %d\n", want);
+      ok = false;
+    }
+  }
+  ~DeviceGuard() { if (ok && prev != want) cudaSetDevice(prev); }
+};
+
 struct DevCoo {
   int N = 0;
   uint64_t nnz = 0;
@@ -405,12 +419,42 @@ int splatt_b200_tensor_from_csf(splatt_csf const * tensors, int csf_alloc,
   return rc;
 }
 
+int splatt_b200_tensor_shard(splatt_b200_tensor const * whole, int rank, int count, int device,
+                             splatt_b200_tensor ** out) {
+  if (!whole || !out || count < 1 || rank < 0 || rank >= count || whole->shard_count != 1) {
+    fprintf(stderr, "SPLATT: splatt_b200_tensor_shard: needs a whole (unsharded) tensor\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  int prev = 0;
+  SPB200_CUDA_OK(cudaGetDevice(&prev));
+  const int dst = device >= 0 ? device : whole->device;
+  splatt_b200_tensor * T = new splatt_b200_tensor();
+  T->nmodes = whole->nmodes;
+  for (int m = 0; m < whole->nmodes; ++m) { T->dims[m] = whole->dims[m]; T->plan[m] = whole->plan[m]; }
+  T->nnz_total = whole->nnz_total;
+  T->layout = whole->layout;
+  T->shard_rank = rank;
+  T->shard_count = count;
+  T->device = dst;
+  T->streams.resize(whole->streams.size());
+  uint64_t c0 = 0, c1 = 0;
+  spb200_shard_chunks(whole->nnz_total, rank, count, &c0, &c1);
+  int rc = SPLATT_SUCCESS;
+  for (size_t i = 0; i < whole->streams.size() && rc == SPLATT_SUCCESS; ++i)
+    rc = spb200_slice_stream(whole->streams[i], whole->device, c0, c1, dst, &T->streams[i]);
+  cudaSetDevice(prev);
+  if (rc != SPLATT_SUCCESS) { splatt_b200_tensor_free(T); return rc; }
+  *out = T;
+  return SPLATT_SUCCESS;
+}
+
 void splatt_b200_tensor_free(splatt_b200_tensor * t) {
   if (!t) return;
   int prev = 0;
   cudaGetDevice(&prev);
   if (prev != t->device) cudaSetDevice(t->device);
   for (auto & s : t->streams) spb200_free_stream(&s);
+  if (t->cta_done) cudaFree(t->cta_done);
   if (prev != t->device) cudaSetDevice(prev);
   delete t;
 }
@@ -445,6 +489,9 @@ int splatt_b200_mode_info(splatt_b200_tensor const * t, int mode, int ncolumns, 
     // in the index words, so the fptr term is the 4 B/nnz parent word).
     uint64_t b = s.nrec * sizeof(SpRec);
     for (int l = 0; l <= N - 3; ++l) b += s.nnodes[l] * 4;   // node counts are this shard's
+    // root kernels of 4+-mode streams read the level-(N-3) id beside every record (4 B per
+    // nonzero) instead of the up[N-3] node array
+    if (p.kind == SPB200_KIND_ROOT && N >= 4) b += s.nrec * 4 - s.nnodes[N - 3] * 4;
     for (int m = 0; m < N; ++m) b += t->dims[m] * (uint64_t)ncolumns * 8;   // N-1 reads + 1 write
     *alg_bytes = b;
   }
@@ -458,6 +505,8 @@ int splatt_b200_mttkrp(splatt_b200_tensor const * t, int mode, int ncolumns, int
     return SPLATT_ERROR_BADINPUT;
   }
   const ModePlan & p = t->plan[mode];
+  DeviceGuard g(t->device);
+  if (!g.ok) return SPLATT_ERROR_BADINPUT;
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
                               d_out, t->dims[mode], static_cast<cudaStream_t>(stream));
 }
@@ -470,6 +519,8 @@ int splatt_b200_mttkrp_columns(splatt_b200_tensor const * t, int mode, int ncolu
     return SPLATT_ERROR_BADINPUT;
   }
   const ModePlan & p = t->plan[mode];
+  DeviceGuard g(t->device);
+  if (!g.ok) return SPLATT_ERROR_BADINPUT;
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
                               d_out, t->dims[mode], static_cast<cudaStream_t>(stream), false,
                               col_begin, col_count);
@@ -482,8 +533,35 @@ int splatt_b200_mttkrp_multicast(splatt_b200_tensor const * t, int mode, int nco
     return SPLATT_ERROR_BADINPUT;
   }
   const ModePlan & p = t->plan[mode];
+  DeviceGuard g(t->device);
+  if (!g.ok) return SPLATT_ERROR_BADINPUT;
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
                               mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true);
+}
+
+int splatt_b200_mttkrp_multicast_sync(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
+                                      double const * const * d_mats, double * mc_out,
+                                      splatt_b200_group_sync const * sync, void * stream) {
+  if (!t || !d_mats || !mc_out || !sync || !sync->mc_flag || !sync->local_flag ||
+      mode < 0 || mode >= t->nmodes) {
+    fprintf(stderr, "SPLATT: splatt_b200_mttkrp_multicast_sync: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const ModePlan & p = t->plan[mode];
+  DeviceGuard g(t->device);
+  if (!g.ok) return SPLATT_ERROR_BADINPUT;
+  if (!t->cta_done) {
+    // finished-CTA counter of the in-kernel barrier (zero between launches)
+    splatt_b200_tensor * tm = const_cast<splatt_b200_tensor *>(t);
+    SPB200_CUDA_OK(cudaMalloc(&tm->cta_done, 64));
+    SPB200_CUDA_OK(cudaMemset(tm->cta_done, 0, 64));
+  }
+  GroupSync gs;
+  gs.mc_flag = sync->mc_flag; gs.local_flag = sync->local_flag; gs.cta_done = t->cta_done;
+  gs.target = sync->target;
+  return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
+                              mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true, 0, 0,
+                              &gs);
 }
 
 int splatt_b200_csf_alloc(int nmodes, uint64_t const * dims, uint64_t nnz,

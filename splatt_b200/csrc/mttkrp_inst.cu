@@ -7,31 +7,43 @@
 #endif
 
 int spb200_root_batch();
+int spb200_root_minb();
 
 namespace spb200 {
 
-template <int N, int L, int KIND, int BATCH, bool KT = false, bool MC = false, int MINB = 0>
+template <int N, int L, int KIND, int BATCH, bool KT = false, bool MC = false, int MINB = 0,
+          int STAGES = kStages>
 static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t stream) {
   auto kern = [] {
     if constexpr (MINB == 0) return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC>;
-    else return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC, MINB>;
+    else return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC, MINB, STAGES>;
   }();
-  static int occ = 0;   // per-variant, set once
-  if (occ == 0) {
+  static_assert(MINB != 0 || STAGES == kStages, "a non-default ring depth needs an explicit MINB");
+  constexpr size_t smem = smem_bytes(STAGES, KIND == SPB200_KIND_ROOT && N >= 4);
+  // function attributes and occupancy are per DEVICE: cache them per ordinal
+  static int occ_of[64] = {0};
+  int dev = 0;
+  SPB200_CUDA_OK(cudaGetDevice(&dev));
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (occ_of[slot] == 0 || dev != slot) {
     SPB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kSmemBytes)));
+                                        static_cast<int>(smem)));
     int o = 0;
-    SPB200_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, kSmemBytes));
-    occ = o > 0 ? o : 1;
+    SPB200_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem));
+    occ_of[slot] = o > 0 ? o : 1;
   }
+  const int occ = occ_of[slot];
   constexpr int G = 32 / L;
   // never launch more groups than there are chunks
   unsigned long long want = (static_cast<unsigned long long>(args.nchunks) + kWarps * G - 1) / (kWarps * G);
   unsigned long long grid = static_cast<unsigned long long>(num_sms) * occ;
   if (grid > want) grid = want;
-  if (grid == 0) return SPLATT_SUCCESS;
-  kern<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(args);
-  ++g_spb200_launches;
+  if (grid == 0) {
+    if (args.sync_mc == nullptr) return SPLATT_SUCCESS;
+    grid = 1;                      // an empty shard still takes part in the group barrier
+  }
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(args);
+  spb200_count_launches(1);
   SPB200_CUDA_OK(cudaGetLastError());
   return SPLATT_SUCCESS;
 }
@@ -42,6 +54,19 @@ static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStrea
     case SPB200_KIND_ROOT:
       if (args.multicast) return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, true>(args, num_sms, stream);
       if (spb200_root_batch() >= 8) return launch_variant<N, L, SPB200_KIND_ROOT, 8>(args, num_sms, stream);
+      if constexpr (N == 4) {   // tuning variants of the 4-mode kernel (SPLATT_B200_BATCH / _MINB)
+        const int b = spb200_root_batch(), mb = spb200_root_minb();
+        if (b == 3 && mb == 3) return launch_variant<N, L, SPB200_KIND_ROOT, 3, false, false, 3>(args, num_sms, stream);
+        if (b == 3) return launch_variant<N, L, SPB200_KIND_ROOT, 3, false, false, 2>(args, num_sms, stream);
+        if (b == 4 && mb == 3) return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, false, 3>(args, num_sms, stream);
+        if (b == 2 && mb == 4) return launch_variant<N, L, SPB200_KIND_ROOT, 2, false, false, 4, 2>(args, num_sms, stream);
+      }
+      if constexpr (N == 3) {   // 32 warps per SM: 4 CTAs of <= 64 registers
+        if (spb200_root_batch() == 2 && spb200_root_minb() == 4)
+          return launch_variant<N, L, SPB200_KIND_ROOT, 2, false, false, 4>(args, num_sms, stream);
+        if (spb200_root_batch() == 4 && spb200_root_minb() == 4)
+          return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, false, 4>(args, num_sms, stream);
+      }
       // deeper trees hold a third gathered row per record: two-record batches keep the
       // kernel at 80 registers / 3 CTAs per SM (measured 1014 vs 1052 us on config 3)
       if (spb200_root_batch() == 2 || (spb200_root_batch() == 0 && N >= 4))

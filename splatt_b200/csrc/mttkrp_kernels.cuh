@@ -35,10 +35,28 @@ namespace spb200 {
 constexpr int kThreads   = 256;
 constexpr int kWarps     = kThreads / 32;
 constexpr int kStageRecs = 128;   // records per warp per stage (2 KB)
-constexpr int kStages    = 3;
+constexpr int kStages    = 3;     // default ring depth (a template parameter of the kernel)
 
-constexpr size_t kSmemBytes =
-    sizeof(SpRec) * kWarps * kStages * kStageRecs + sizeof(uint64_t) * kWarps * kStages;
+// Shared-memory layout.  Every lane group owns one region per stage; the regions of the
+// groups of a warp are staggered by 16 bytes (one pad record / four pad ids per region), so
+// that the per-group broadcast reads of one warp instruction (LDS.128 of G different
+// records, LDS.32 of G different ids) fall into different banks.  Without the stagger the
+// regions are a multiple of 128 bytes apart and every such read is a G-way bank conflict
+// (measured: 1.0 / 1.4 shared-memory wavefronts per record for 3 / 4 modes instead of
+// 0.5 / 0.35 -- 20 % / 38 % of the L1 data-pipe load of the kernel).
+constexpr int kRecPad = 8;        // pad records per warp-stage (>= groups per warp)
+constexpr int kAncPad = 32;       // pad ids per warp-stage (4 per group)
+__host__ __device__ constexpr size_t smem_rec_bytes(int stages) {
+  return sizeof(SpRec) * kWarps * stages * (kStageRecs + kRecPad);
+}
+__host__ __device__ constexpr size_t smem_bar_bytes(int stages) { return sizeof(uint64_t) * kWarps * stages; }
+// N >= 4 root kernels also stage the per-record level-(N-3) ancestor ids (4 B each)
+__host__ __device__ constexpr size_t smem_anc_bytes(int stages) {
+  return sizeof(uint32_t) * kWarps * stages * (kStageRecs + kAncPad);
+}
+__host__ __device__ constexpr size_t smem_bytes(int stages, bool anc) {
+  return smem_rec_bytes(stages) + smem_bar_bytes(stages) + (anc ? smem_anc_bytes(stages) : 0);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -159,17 +177,25 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
   }
 }
 
-template <int N, int L, int KIND, int BATCH, bool KT, bool MC, int MINB = ((BATCH >= 8 || N >= 4) ? 2 : 3)>
+template <int N, int L, int KIND, int BATCH, bool KT, bool MC, int MINB = ((BATCH >= 8 || N >= 4) ? 2 : 3),
+          int STAGES = kStages>
 __global__ void __launch_bounds__(kThreads, MINB)
 mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 2 && N <= SPB200_MAXN, "2..8 modes");
   constexpr int G  = 32 / L;            // groups per warp
   constexpr int SU = kStageRecs / G;    // records per group per stage
+  constexpr int RS = SU + 1;            // region stride in records (16-byte stagger)
+  constexpr int AS = SU + 4;            // region stride in ancestor ids (16-byte stagger)
+  constexpr int kStages = STAGES;       // shadows the namespace default inside the kernel
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpRec *    srec = reinterpret_cast<SpRec *>(smem_raw);
-  uint64_t * bars =
-      reinterpret_cast<uint64_t *>(smem_raw + sizeof(SpRec) * kWarps * kStages * kStageRecs);
+  uint64_t * bars = reinterpret_cast<uint64_t *>(smem_raw + smem_rec_bytes(STAGES));
+  // level-(N-3) ancestor id of every record, staged beside the records (root, N >= 4): all
+  // three row gathers of a record then depend on shared memory only -- no id -> row chain
+  constexpr bool kAnc = (KIND == SPB200_KIND_ROOT && N >= 4);
+  uint32_t * sanc =
+      reinterpret_cast<uint32_t *>(smem_raw + smem_rec_bytes(STAGES) + smem_bar_bytes(STAGES));
 
   const int      warp   = threadIdx.x >> 5;
   const int      lane   = threadIdx.x & 31;
@@ -210,8 +236,14 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
         // generic-proxy accesses to this stage (record reads, the range-end patch) are
         // ordered before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_expect_tx(bar, cnt * 16u);
-        tma_bulk_g2s(&srec[((warp * kStages + st) * G + grp) * SU], a.rec + rb + off, cnt * 16u,
+        if constexpr (kAnc) {
+          const uint32_t ab = (cnt * 4u + 15u) & ~15u;     // the array is padded to 16 B
+          mbar_arrive_expect_tx(bar, cnt * 16u + ab);
+          tma_bulk_g2s(&sanc[((warp * kStages + st) * G + grp) * AS], a.anc + rb + off, ab, bar);
+        } else {
+          mbar_arrive_expect_tx(bar, cnt * 16u);
+        }
+        tma_bulk_g2s(&srec[((warp * kStages + st) * G + grp) * RS], a.rec + rb + off, cnt * 16u,
                      bar);
       } else {
         mbar_arrive(bar);
@@ -251,7 +283,8 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
 
     const uint32_t off = step * SU;
     const uint32_t cnt = (off < T) ? min(static_cast<uint32_t>(SU), T - off) : 0u;
-    SpRec *        buf = &srec[((warp * kStages + st) * G + grp) * SU];
+    SpRec *        buf = &srec[((warp * kStages + st) * G + grp) * RS];
+    const uint32_t * abuf = &sanc[((warp * kStages + st) * G + grp) * AS];
     // The last record of the range closes every level (range boundary).
     if (leader && cnt && off + cnt == T)
       buf[cnt - 1].aux = (buf[cnt - 1].aux & SPB200_IDX_MASK) | (uint32_t(N - 1) << SPB200_IDX_BITS);
@@ -299,16 +332,15 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
                         : ld_row(mbase[N - 2], q[u].w & SPB200_IDX_MASK, pitch);
           uint32_t p2 = 0;
           if constexpr (N >= 4) {
-            // level N-3 closes are frequent on deep trees: their ids are the next
-            // entries of up[N-3]; fetch ids, then rows, for the whole batch
-            uint32_t idx2[BATCH];
+            // level N-3 closes are frequent on deep trees; the id of the closing node rides
+            // beside the record, so its row gather is issued together with the other two
             p2 = pos[N - 3];
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
-              if ((q[u].w >> SPB200_IDX_BITS) >= 2u) { idx2[u] = __ldg(&a.up[N - 3][p2]); ++p2; }
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u)
-              if ((q[u].w >> SPB200_IDX_BITS) >= 2u) r2[u] = ld_row(mbase[N - 3], idx2[u], pitch);
+              if ((q[u].w >> SPB200_IDX_BITS) >= 2u) {
+                r2[u] = ld_row(mbase[N - 3], abuf[n0 + u], pitch);
+                ++p2;
+              }
           }
           constexpr uint32_t kFast = (N >= 4) ? 3u : 2u;   // close counts handled branch-free
           if ((hi >> SPB200_IDX_BITS) < kFast) {
@@ -343,8 +375,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
           double2       r = zero2, r2 = zero2;
           if (q.w >> SPB200_IDX_BITS) r = ld_row(mbase[N - 2], q.w & SPB200_IDX_MASK, pitch);
           if constexpr (N >= 4) {
-            if ((q.w >> SPB200_IDX_BITS) >= 2u)
-              r2 = ld_row(mbase[N - 3], __ldg(&a.up[N - 3][pos[N - 3]]), pitch);
+            if ((q.w >> SPB200_IDX_BITS) >= 2u) r2 = ld_row(mbase[N - 3], abuf[n0], pitch);
           }
           root_record<N, MC>(a, q, b, r, r2, acc, pos, mbase, obase, pitch);
         }
@@ -430,6 +461,27 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
 
     __syncwarp();
     if (step + kStages < wsteps) issue(step + kStages);
+  }
+
+  if constexpr (MC) {
+    // Group barrier in the kernel's tail (see MttkrpArgs::sync_*).
+    if (a.sync_mc != nullptr) {
+      __threadfence_system();                 // this thread's multimem.red's are performed
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(a.sync_cta, 1u);
+        if (done == gridDim.x - 1) {          // last CTA of this GPU
+          *reinterpret_cast<volatile unsigned int *>(a.sync_cta) = 0u;   // ready for the next launch
+          __threadfence_system();
+          asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;"
+                       ::"l"(a.sync_mc), "r"(1u) : "memory");
+          unsigned int v;
+          do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.sync_local) : "memory");
+          } while (static_cast<int>(v - a.sync_target) < 0);
+        }
+      }
+    }
   }
 }
 

@@ -259,11 +259,13 @@ int spb200_launch_tiled_root3(const FiberStream & s, int ncolumns, int ldm, uint
   const unsigned grid = s.kranges;
 #define SPB200_TILED_LAUNCH(LL)                                                                   \
   do {                                                                                            \
-    static bool set = false;                                                                      \
-    if (!set) {                                                                                   \
+    static bool set[64] = {false};          /* function attributes are per device */            \
+    int dev_ = 0;                                                                                 \
+    SPB200_CUDA_OK(cudaGetDevice(&dev_));                                                         \
+    if (dev_ < 0 || dev_ >= 64 || !set[dev_]) {                                                   \
       SPB200_CUDA_OK(cudaFuncSetAttribute(mttkrp_tiled_root3<LL>,                                 \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      set = true;                                                                                 \
+      if (dev_ >= 0 && dev_ < 64) set[dev_] = true;                                               \
     }                                                                                             \
     mttkrp_tiled_root3<LL><<<grid, threads, smem, stream>>>(a);                                   \
   } while (0)
@@ -272,7 +274,7 @@ int spb200_launch_tiled_root3(const FiberStream & s, int ncolumns, int ldm, uint
   else if (a.ncols <= 32) SPB200_TILED_LAUNCH(16);
   else SPB200_TILED_LAUNCH(32);
 #undef SPB200_TILED_LAUNCH
-  ++g_spb200_launches;
+  spb200_count_launches(1);
   SPB200_CUDA_OK(cudaGetLastError());
   return SPLATT_SUCCESS;
 }

@@ -1,0 +1,733 @@
+// Single-process multi-GPU engine: ONE host process drives k GPUs of one NVSwitch box.
+//
+// This is the C-ABI counterpart of the reference's distributed driver
+// (mpi_cpd_als_iterate, src/mpi/mpi_cpd.c:627-804; per-mode reduction :250-308) for one
+// node: the tensor is partitioned, every device computes the MTTKRP of its share, the
+// output factor is summed over devices once per mode, the dense tail runs replicated.
+// Differences that make it B200-native:
+//   * partition = equal-nnz contiguous chunk ranges of every fiber stream (built once on
+//     the first device, the shares are cut out and moved device-to-device);
+//   * exchange  = inside the MTTKRP kernel: every finished output row is added into ALL
+//     devices' buffers with multimem.red.add.f64 on an NVLink multicast mapping created
+//     here with the CUDA driver's multicast objects (no NCCL, no torch), and the group
+//     barrier is the kernel's own tail (mttkrp_kernels.cuh);
+//   * fallback  = when the box has no multicast support: local kernels, then a peer-memory
+//     reduce kernel (each device sums one row slice over all peers' partials and writes
+//     the sum into every peer's result buffer), ordered with CUDA events.
+#include "common.h"
+#include <cuda.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+// cpd.cu
+double spb200_cpd_rand_val();
+void   spb200_cpd_postprocess(double ** mats, const uint64_t * dims, int N, int R, double * lambda);
+double spb200_csf_frobsq(const splatt_csf * t);
+
+namespace {
+
+constexpr int kMaxDev = 16;
+
+// ---------------------------------------------------------------------------
+// Driver entry points, resolved through the runtime (no link dependency on libcuda:
+// the library must load on a machine without a GPU driver).
+// ---------------------------------------------------------------------------
+#define SPB200_DRV_LIST(X)        \
+  X(cuDeviceGet)                  \
+  X(cuDeviceGetAttribute)         \
+  X(cuMulticastCreate)            \
+  X(cuMulticastAddDevice)         \
+  X(cuMulticastBindMem)           \
+  X(cuMulticastUnbind)            \
+  X(cuMulticastGetGranularity)    \
+  X(cuMemCreate)                  \
+  X(cuMemRelease)                 \
+  X(cuMemAddressReserve)          \
+  X(cuMemAddressFree)             \
+  X(cuMemMap)                     \
+  X(cuMemUnmap)                   \
+  X(cuMemSetAccess)               \
+  X(cuMemGetAllocationGranularity)
+
+struct Drv {
+#define X(name) decltype(&name) name##_ = nullptr;
+  SPB200_DRV_LIST(X)
+#undef X
+  bool ok = false;
+};
+
+const Drv & drv() {
+  static Drv d;
+  static bool tried = false;
+  if (tried) return d;
+  tried = true;
+  bool ok = true;
+#define X(name)                                                                              \
+  {                                                                                          \
+    void * fp = nullptr;                                                                     \
+    cudaDriverEntryPointQueryResult qr;                                                      \
+    if (cudaGetDriverEntryPoint(#name, &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp || \
+        qr != cudaDriverEntryPointSuccess) {                                                 \
+      ok = false;                                                                            \
+      cudaGetLastError();                                                                    \
+    }                                                                                        \
+    d.name##_ = reinterpret_cast<decltype(&name)>(fp);                                       \
+  }
+  SPB200_DRV_LIST(X)
+#undef X
+  d.ok = ok;
+  return d;
+}
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One region of `bytes` on every device, all bound to one multicast object:
+// uc[d] = device d's own (unicast) address of its copy, mc = the multicast address.
+struct McRegion {
+  int k = 0;
+  size_t bytes = 0;
+  CUmemGenericAllocationHandle mch = 0;
+  CUmemGenericAllocationHandle mem[kMaxDev] = {0};
+  CUdeviceptr mc = 0;
+  CUdeviceptr uc[kMaxDev] = {0};
+  CUdevice cud[kMaxDev] = {0};
+  bool bound[kMaxDev] = {false};
+  bool mc_mapped = false, uc_mapped[kMaxDev] = {false};
+
+  bool create(int k_, const int * devs, size_t want, int verbosity) {
+    const Drv & D = drv();
+    if (!D.ok) { if (verbosity > 1) fprintf(stderr, "SPLATT-B200: driver entry points unavailable\n"); return false; }
+    k = k_;
+    for (int i = 0; i < k; ++i) {
+      for (int j = 0; j < i; ++j)
+        if (devs[j] == devs[i]) return false;            // a device can join a team once
+      if (cudaSetDevice(devs[i]) != cudaSuccess || cudaFree(0) != cudaSuccess) return false;
+      if (D.cuDeviceGet_(&cud[i], devs[i]) != CUDA_SUCCESS) return false;
+      int sup = 0;
+      if (D.cuDeviceGetAttribute_(&sup, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cud[i]) != CUDA_SUCCESS || !sup) {
+        if (verbosity > 1) fprintf(stderr, "SPLATT-B200: device %d has no multicast support\n", devs[i]);
+        return false;
+      }
+    }
+    // every step reports its CUresult on failure: the caller falls back to the peer reduce
+#define MC_TRY(call)                                                                       \
+    do {                                                                                     \
+      CUresult r_ = (call);                                                                  \
+      if (r_ != CUDA_SUCCESS) {                                                              \
+        fprintf(stderr, "SPLATT-B200: multicast set-up: %s -> CUresult %d\n", #call, (int)r_); \
+        destroy();                                                                           \
+        return false;                                                                        \
+      }                                                                                      \
+    } while (0)
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.numDevices = (unsigned)k;
+    mp.handleTypes = 0;
+    mp.flags = 0;
+    mp.size = want;
+    size_t gran = 0;
+    MC_TRY(D.cuMulticastGetGranularity_(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+    if (!gran) return false;
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = cud[0];
+    size_t g2 = 0;
+    if (D.cuMemGetAllocationGranularity_(&g2, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && g2 > gran)
+      gran = g2;
+    bytes = round_up(want, gran);
+    mp.size = bytes;
+    MC_TRY(D.cuMulticastCreate_(&mch, &mp));
+    for (int i = 0; i < k; ++i) MC_TRY(D.cuMulticastAddDevice_(mch, cud[i]));
+    for (int i = 0; i < k; ++i) {
+      ap.location.id = cud[i];
+      MC_TRY(D.cuMemCreate_(&mem[i], bytes, &ap, 0));
+      MC_TRY(D.cuMulticastBindMem_(mch, 0, mem[i], 0, bytes, 0));
+      bound[i] = true;
+      MC_TRY(D.cuMemAddressReserve_(&uc[i], bytes, gran, 0, 0));
+      MC_TRY(D.cuMemMap_(uc[i], bytes, 0, mem[i], 0));
+      uc_mapped[i] = true;
+      CUmemAccessDesc ad;
+      memset(&ad, 0, sizeof(ad));
+      ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      ad.location.id = cud[i];
+      ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      MC_TRY(D.cuMemSetAccess_(uc[i], bytes, &ad, 1));
+    }
+    MC_TRY(D.cuMemAddressReserve_(&mc, bytes, gran, 0, 0));
+    MC_TRY(D.cuMemMap_(mc, bytes, 0, mch, 0));
+    mc_mapped = true;
+    CUmemAccessDesc ads[kMaxDev];
+    memset(ads, 0, sizeof(ads));
+    for (int i = 0; i < k; ++i) {
+      ads[i].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      ads[i].location.id = cud[i];
+      ads[i].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    }
+    MC_TRY(D.cuMemSetAccess_(mc, bytes, ads, (size_t)k));
+#undef MC_TRY
+    return true;
+  }
+
+  void destroy() {
+    const Drv & D = drv();
+    if (!D.ok) return;
+    if (mc) {
+      if (mc_mapped) D.cuMemUnmap_(mc, bytes);
+      D.cuMemAddressFree_(mc, bytes);
+      mc = 0; mc_mapped = false;
+    }
+    for (int i = 0; i < k; ++i) {
+      if (uc[i]) {
+        if (uc_mapped[i]) D.cuMemUnmap_(uc[i], bytes);
+        D.cuMemAddressFree_(uc[i], bytes);
+        uc[i] = 0; uc_mapped[i] = false;
+      }
+      if (bound[i]) {
+        D.cuMulticastUnbind_(mch, cud[i], 0, bytes);
+        bound[i] = false;
+      }
+      if (mem[i]) { D.cuMemRelease_(mem[i]); mem[i] = 0; }
+    }
+    if (mch) { D.cuMemRelease_(mch); mch = 0; }
+  }
+};
+
+struct PeerReduceArgs {
+  const double2 * part[kMaxDev];
+  double2 *       res[kMaxDev];
+  int             k;
+};
+
+// Fallback exchange: sum the partial outputs of all devices over the element range
+// [e0, e1) (double2 units) and write the sum into every device's result buffer.
+__global__ void k_peer_reduce(const PeerReduceArgs a, unsigned long long e0, unsigned long long e1) {
+  for (unsigned long long i = e0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < e1;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    double2 s = a.part[0][i];
+    for (int p = 1; p < a.k; ++p) {
+      const double2 v = a.part[p][i];
+      s.x += v.x; s.y += v.y;
+    }
+    for (int p = 0; p < a.k; ++p) a.res[p][i] = s;
+  }
+}
+
+struct DevState {
+  int dev = 0;
+  splatt_b200_tensor * T = nullptr;
+  cudaStream_t stream = nullptr;
+  double * mats[SPB200_MAXN] = {nullptr};   // factor replicas, dims[m] x ldm
+  double * out[SPB200_MAXN] = {nullptr};    // this device's (unicast) output buffer per mode
+  double * part = nullptr;                  // fallback: local partial, maxdim x ldm
+  uint32_t * flag_local = nullptr;
+  cudaEvent_t ev_k = nullptr, ev_r = nullptr;
+  splatt_b200_als_tail * tail = nullptr;
+};
+
+#define MCK(call)                                                                               \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      fprintf(stderr, "SPLATT: CUDA error '%s' at %s:%d (%s)\n", cudaGetErrorString(e_),       \
+              __FILE__, __LINE__, #call);                                                       \
+      return (e_ == cudaErrorMemoryAllocation) ? SPLATT_ERROR_NOMEMORY : SPLATT_ERROR_BADINPUT; \
+    }                                                                                           \
+  } while (0)
+
+}  // namespace
+
+struct splatt_b200_multi {
+  int k = 0;
+  int N = 0;
+  uint64_t dims[SPB200_MAXN] = {0};
+  uint64_t maxdim = 0;
+  uint64_t nnz = 0;
+  int R = 0, ldm = 0;
+  bool multicast = false;
+  bool distinct = true;            // all devices distinct (false only in tests: "0,0")
+  McRegion mc;
+  size_t out_off[SPB200_MAXN] = {0};
+  double * mc_out[SPB200_MAXN] = {nullptr};
+  uint32_t * mc_flag = nullptr;
+  uint32_t epoch = 0;
+  DevState d[kMaxDev];
+  int prev_dev = 0;
+  double last_ms = 0;
+  // page-locked bounce buffers for pageable caller memory (see dropin.cu)
+  double * stage_in = nullptr;  size_t stage_in_cap = 0;
+  double * stage_out = nullptr; size_t stage_out_cap = 0;
+};
+
+namespace {
+
+int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
+  const int k = h->k, N = h->N;
+  int devs[kMaxDev];
+  for (int i = 0; i < k; ++i) devs[i] = h->d[i].dev;
+  // multicast region: [flags 4 KB][out mode 0][out mode 1]...
+  size_t off = 4096;
+  for (int m = 0; m < N; ++m) {
+    h->out_off[m] = off;
+    off += round_up(h->dims[m] * (size_t)h->ldm * 8, 4096);
+  }
+  const char * me = getenv("SPLATT_B200_MULTICAST");
+  const bool want_mc = !(me && atoi(me) == 0) && h->distinct && k > 1;
+  h->multicast = want_mc && h->mc.create(k, devs, off, verbosity);
+  if (want_mc && !h->multicast && verbosity > 0)
+    fprintf(stderr, "SPLATT-B200: NVLink multicast unavailable; using the peer-memory reduce\n");
+  for (int i = 0; i < k; ++i) {
+    DevState & s = h->d[i];
+    MCK(cudaSetDevice(s.dev));
+    MCK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    MCK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+    MCK(cudaEventCreateWithFlags(&s.ev_r, cudaEventDisableTiming));
+    for (int m = 0; m < N; ++m) {
+      MCK(cudaMalloc(&s.mats[m], h->dims[m] * (size_t)h->ldm * 8));
+      MCK(cudaMemset(s.mats[m], 0, h->dims[m] * (size_t)h->ldm * 8));
+    }
+    if (h->multicast) {
+      char * base = reinterpret_cast<char *>(h->mc.uc[i]);
+      MCK(cudaMemset(base, 0, h->mc.bytes));
+      s.flag_local = reinterpret_cast<uint32_t *>(base);
+      for (int m = 0; m < N; ++m) s.out[m] = reinterpret_cast<double *>(base + h->out_off[m]);
+    } else {
+      MCK(cudaMalloc(&s.part, h->maxdim * (size_t)h->ldm * 8));
+      for (int m = 0; m < N; ++m) MCK(cudaMalloc(&s.out[m], h->dims[m] * (size_t)h->ldm * 8));
+    }
+    MCK(cudaDeviceSynchronize());
+  }
+  if (h->multicast) {
+    char * mb = reinterpret_cast<char *>(h->mc.mc);
+    h->mc_flag = reinterpret_cast<uint32_t *>(mb);
+    for (int m = 0; m < N; ++m) h->mc_out[m] = reinterpret_cast<double *>(mb + h->out_off[m]);
+  } else if (h->distinct && k > 1) {
+    for (int i = 0; i < k; ++i) {
+      MCK(cudaSetDevice(h->d[i].dev));
+      for (int j = 0; j < k; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        MCK(cudaDeviceCanAccessPeer(&can, h->d[i].dev, h->d[j].dev));
+        if (!can) {
+          fprintf(stderr, "SPLATT: devices %d and %d have no peer access\n", h->d[i].dev, h->d[j].dev);
+          return SPLATT_ERROR_BADINPUT;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(h->d[j].dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MCK(e);
+        cudaGetLastError();
+      }
+    }
+  }
+  return SPLATT_SUCCESS;
+}
+
+// One MTTKRP over all devices; on return (in stream order of every device) out[d][mode]
+// holds the full sum on every device.
+int multi_mttkrp_enqueue(splatt_b200_multi * h, int mode) {
+  const int k = h->k;
+  if (h->multicast) {
+    ++h->epoch;
+    for (int i = 0; i < k; ++i) {
+      DevState & s = h->d[i];
+      splatt_b200_group_sync gs;
+      gs.mc_flag = h->mc_flag;
+      gs.local_flag = s.flag_local;
+      gs.target = h->epoch * (uint32_t)k;
+      gs.reserved = 0;
+      int rc = splatt_b200_mttkrp_multicast_sync(s.T, mode, h->R, h->ldm, s.mats, h->mc_out[mode],
+                                                 &gs, s.stream);
+      if (rc != SPLATT_SUCCESS) return rc;
+    }
+    return SPLATT_SUCCESS;
+  }
+  // fallback: local partials, then the peer reduce
+  for (int i = 0; i < k; ++i) {
+    DevState & s = h->d[i];
+    int rc = splatt_b200_mttkrp(s.T, mode, h->R, h->ldm, s.mats, k > 1 ? s.part : s.out[mode], s.stream);
+    if (rc != SPLATT_SUCCESS) return rc;
+    if (k > 1) { MCK(cudaSetDevice(s.dev)); MCK(cudaEventRecord(s.ev_k, s.stream)); }
+  }
+  if (k == 1) return SPLATT_SUCCESS;
+  PeerReduceArgs a;
+  a.k = k;
+  for (int p = 0; p < k; ++p) {
+    a.part[p] = reinterpret_cast<const double2 *>(h->d[p].part);
+    a.res[p] = reinterpret_cast<double2 *>(h->d[p].out[mode]);
+  }
+  const unsigned long long I = h->dims[mode], half = (unsigned long long)h->ldm / 2;
+  for (int i = 0; i < k; ++i) {
+    DevState & s = h->d[i];
+    MCK(cudaSetDevice(s.dev));
+    for (int p = 0; p < k; ++p)
+      if (p != i) MCK(cudaStreamWaitEvent(s.stream, h->d[p].ev_k, 0));
+    const unsigned long long e0 = I * i / k * half, e1 = I * (i + 1) / k * half;
+    if (e1 > e0) {
+      const unsigned blocks = (unsigned)std::min<unsigned long long>((e1 - e0 + 255) / 256, 148ull * 8);
+      k_peer_reduce<<<blocks, 256, 0, s.stream>>>(a, e0, e1);
+      spb200_count_launches(1);
+      MCK(cudaGetLastError());
+    }
+    MCK(cudaEventRecord(s.ev_r, s.stream));
+  }
+  for (int i = 0; i < k; ++i) {
+    DevState & s = h->d[i];
+    MCK(cudaSetDevice(s.dev));
+    for (int p = 0; p < k; ++p)
+      if (p != i) MCK(cudaStreamWaitEvent(s.stream, h->d[p].ev_r, 0));
+  }
+  return SPLATT_SUCCESS;
+}
+
+// Result of `mode` consumed on device i: make its buffer ready for the next use.
+int multi_release(splatt_b200_multi * h, int i, int mode) {
+  if (!h->multicast) return SPLATT_SUCCESS;
+  DevState & s = h->d[i];
+  MCK(cudaSetDevice(s.dev));
+  MCK(cudaMemsetAsync(s.out[mode], 0, h->dims[mode] * (size_t)h->ldm * 8, s.stream));
+  return SPLATT_SUCCESS;
+}
+
+bool host_pinned(const void * p, size_t bytes) {
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a0.type != cudaMemoryTypeHost) return false;
+  if (bytes <= 1) return true;
+  if (cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a1.type == cudaMemoryTypeHost;
+}
+
+void par_memcpy(void * dst, const void * src, size_t bytes) {
+  const size_t chunk = 1 << 18;
+  const int64_t n = (int64_t)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) num_threads(8)
+  for (int64_t c = 0; c < n; ++c) {
+    const size_t o = (size_t)c * chunk;
+    memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, std::min(chunk, bytes - o));
+  }
+}
+
+int parse_devices(int * devs) {
+  // SPLATT_B200_DEVICES="0,1,2,3" wins; else SPLATT_B200_NGPUS=k -> devices 0..k-1
+  int n = 0;
+  const char * dl = getenv("SPLATT_B200_DEVICES");
+  if (dl && *dl) {
+    const char * p = dl;
+    while (*p && n < kMaxDev) {
+      char * end = nullptr;
+      long v = strtol(p, &end, 10);
+      if (end == p) break;
+      devs[n++] = (int)v;
+      p = (*end == ',') ? end + 1 : end;
+    }
+    return n;
+  }
+  const char * ng = getenv("SPLATT_B200_NGPUS");
+  if (ng && atoi(ng) > 1) {
+    n = std::min(atoi(ng), kMaxDev);
+    for (int i = 0; i < n; ++i) devs[i] = i;
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int splatt_b200_multi_env_devices(int * devices, int cap) {
+  int devs[kMaxDev];
+  const int n = parse_devices(devs);
+  for (int i = 0; i < n && i < cap; ++i) devices[i] = devs[i];
+  return n;
+}
+
+void splatt_b200_multi_free(splatt_b200_multi * h) {
+  if (!h) return;
+  for (int i = 0; i < h->k; ++i) {
+    DevState & s = h->d[i];
+    cudaSetDevice(s.dev);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  }
+  for (int i = 0; i < h->k; ++i) {
+    DevState & s = h->d[i];
+    cudaSetDevice(s.dev);
+    if (s.tail) splatt_b200_als_tail_free(s.tail);
+    for (int m = 0; m < SPB200_MAXN; ++m) {
+      if (s.mats[m]) cudaFree(s.mats[m]);
+      if (!h->multicast && s.out[m]) cudaFree(s.out[m]);
+    }
+    if (s.part) cudaFree(s.part);
+    if (s.ev_k) cudaEventDestroy(s.ev_k);
+    if (s.ev_r) cudaEventDestroy(s.ev_r);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.T) splatt_b200_tensor_free(s.T);
+  }
+  if (h->multicast) h->mc.destroy();
+  if (h->stage_in) cudaFreeHost(h->stage_in);
+  if (h->stage_out) cudaFreeHost(h->stage_out);
+  cudaSetDevice(h->prev_dev);
+  delete h;
+}
+
+int splatt_b200_multi_create(splatt_csf const * tensors, int csf_alloc, int ncolumns,
+                             int const * devices, int ndevices, int verbosity,
+                             splatt_b200_multi ** out) {
+  if (!tensors || !out || ncolumns < 1 || !devices || ndevices < 1 || ndevices > kMaxDev) {
+    fprintf(stderr, "SPLATT: splatt_b200_multi_create: bad arguments\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  int ndev_sys = 0;
+  MCK(cudaGetDeviceCount(&ndev_sys));
+  for (int i = 0; i < ndevices; ++i)
+    if (devices[i] < 0 || devices[i] >= ndev_sys) {
+      fprintf(stderr, "SPLATT: CUDA device %d requested, %d present\n", devices[i], ndev_sys);
+      return SPLATT_ERROR_BADINPUT;
+    }
+  splatt_b200_multi * h = new splatt_b200_multi();
+  cudaGetDevice(&h->prev_dev);
+  h->k = ndevices;
+  h->N = (int)tensors[0].nmodes;
+  h->R = ncolumns;
+  h->ldm = ncolumns + (ncolumns & 1);
+  h->nnz = tensors[0].nnz;
+  for (int m = 0; m < h->N; ++m) {
+    h->dims[m] = tensors[0].dims[m];
+    h->maxdim = std::max(h->maxdim, h->dims[m]);
+  }
+  for (int i = 0; i < ndevices; ++i) {
+    h->d[i].dev = devices[i];
+    for (int j = 0; j < i; ++j)
+      if (devices[j] == devices[i]) h->distinct = false;
+  }
+  // 1. whole tensor on the first device (one upload, one sort per stream) ...
+  splatt_b200_build_opts bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.layout = SPLATT_B200_LAYOUT_ALLROOT;   // the fused exchange needs root kernels
+  bo.device = devices[0];
+  bo.verbosity = verbosity;
+  bo.ktile = -1;
+  splatt_b200_tensor * whole = nullptr;
+  int rc = splatt_b200_tensor_from_csf(tensors, csf_alloc, &bo, &whole);
+  // 2. ... cut into equal-nnz shares, moved device to device
+  for (int i = 0; i < ndevices && rc == SPLATT_SUCCESS; ++i)
+    rc = splatt_b200_tensor_shard(whole, i, ndevices, devices[i], &h->d[i].T);
+  if (whole) splatt_b200_tensor_free(whole);
+  if (rc == SPLATT_SUCCESS) rc = multi_alloc_buffers(h, verbosity);
+  if (rc != SPLATT_SUCCESS) { splatt_b200_multi_free(h); return rc; }
+  cudaSetDevice(h->prev_dev);
+  if (verbosity > 1)
+    printf("SPLATT-B200: %d devices, exchange = %s\n", h->k,
+           h->multicast ? "fused NVLink multicast (multimem.red in the MTTKRP kernel)"
+                        : (h->k > 1 ? "peer-memory reduce kernel" : "none"));
+  *out = h;
+  return SPLATT_SUCCESS;
+}
+
+int splatt_b200_multi_info(splatt_b200_multi const * h, int * ndevices, int * multicast,
+                           uint64_t * nnz_local, uint64_t * device_bytes) {
+  if (!h) return SPLATT_ERROR_BADINPUT;
+  if (ndevices) *ndevices = h->k;
+  if (multicast) *multicast = h->multicast ? 1 : 0;
+  for (int i = 0; i < h->k; ++i) {
+    uint64_t nl = 0, db = 0;
+    splatt_b200_tensor_info(h->d[i].T, nullptr, nullptr, nullptr, &nl, &db);
+    if (nnz_local) nnz_local[i] = nl;
+    if (device_bytes) device_bytes[i] = db;
+  }
+  return SPLATT_SUCCESS;
+}
+
+// Host-buffer MTTKRP over all devices (what splatt_mttkrp_csf runs when several GPUs are
+// configured): factors H2D to every device over its own PCIe link, fused kernel +
+// exchange, result D2H as k row slices (one per device, k PCIe links in parallel).
+int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const * const * mats,
+                                  double * out_host) {
+  if (!h || !mats || !out_host || mode < 0 || mode >= h->N) return SPLATT_ERROR_BADINPUT;
+  auto t0 = std::chrono::steady_clock::now();
+  const int k = h->k, N = h->N;
+  const size_t J = (size_t)h->R, ld = (size_t)h->ldm;
+  // pageable caller buffers: one packed copy into page-locked staging serves all k devices
+  bool pinned = host_pinned(out_host, h->dims[mode] * J * 8);
+  size_t in_doubles = 0;
+  for (int m = 0; m < N; ++m)
+    if (m != mode) { pinned = pinned && host_pinned(mats[m], h->dims[m] * J * 8); in_doubles += h->dims[m] * J; }
+  const double * src[SPB200_MAXN] = {nullptr};
+  for (int m = 0; m < N; ++m) src[m] = mats[m];
+  if (!pinned) {
+    if (in_doubles > h->stage_in_cap) {
+      if (h->stage_in) cudaFreeHost(h->stage_in);
+      h->stage_in = nullptr; h->stage_in_cap = 0;
+      MCK(cudaMallocHost(&h->stage_in, in_doubles * 8));
+      h->stage_in_cap = in_doubles;
+    }
+    if (h->dims[mode] * J > h->stage_out_cap) {
+      if (h->stage_out) cudaFreeHost(h->stage_out);
+      h->stage_out = nullptr; h->stage_out_cap = 0;
+      MCK(cudaMallocHost(&h->stage_out, h->dims[mode] * J * 8));
+      h->stage_out_cap = h->dims[mode] * J;
+    }
+  }
+  size_t off = 0;
+  for (int m = 0; m < N; ++m) {
+    if (m == mode) continue;                            // never read (may alias the output)
+    if (!pinned) {
+      par_memcpy(h->stage_in + off, mats[m], h->dims[m] * J * 8);
+      src[m] = h->stage_in + off;
+      off += h->dims[m] * J;
+    }
+    // issue this matrix to every device as soon as it is staged (k PCIe links in parallel)
+    for (int i = 0; i < k; ++i) {
+      DevState & s = h->d[i];
+      MCK(cudaSetDevice(s.dev));
+      if (ld == J)
+        MCK(cudaMemcpyAsync(s.mats[m], src[m], h->dims[m] * J * 8, cudaMemcpyHostToDevice, s.stream));
+      else
+        MCK(cudaMemcpy2DAsync(s.mats[m], ld * 8, src[m], J * 8, J * 8, h->dims[m],
+                              cudaMemcpyHostToDevice, s.stream));
+    }
+  }
+  double * dst_host = pinned ? out_host : h->stage_out;
+  int rc = multi_mttkrp_enqueue(h, mode);
+  if (rc != SPLATT_SUCCESS) return rc;
+  const uint64_t I = h->dims[mode];
+  for (int i = 0; i < k; ++i) {
+    DevState & s = h->d[i];
+    MCK(cudaSetDevice(s.dev));
+    const uint64_t r0 = I * i / k, r1 = I * (i + 1) / k;
+    if (r1 > r0) {
+      if (ld == J)
+        MCK(cudaMemcpyAsync(dst_host + r0 * J, s.out[mode] + r0 * ld, (r1 - r0) * J * 8,
+                            cudaMemcpyDeviceToHost, s.stream));
+      else
+        MCK(cudaMemcpy2DAsync(dst_host + r0 * J, J * 8, s.out[mode] + r0 * ld, ld * 8, J * 8, r1 - r0,
+                              cudaMemcpyDeviceToHost, s.stream));
+    }
+    rc = multi_release(h, i, mode);
+    if (rc != SPLATT_SUCCESS) return rc;
+  }
+  for (int i = 0; i < k; ++i) {
+    MCK(cudaSetDevice(h->d[i].dev));
+    MCK(cudaStreamSynchronize(h->d[i].stream));
+  }
+  if (!pinned) par_memcpy(out_host, h->stage_out, I * J * 8);
+  cudaSetDevice(h->prev_dev);
+  h->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return SPLATT_SUCCESS;
+}
+
+// CPD-ALS over all devices: per mode the fused MTTKRP + exchange, then the dense tail
+// replicated on every device (the same kernels splatt_cpd_als uses on one GPU); the fit and
+// the stop decision come from device 0 only, so every device takes the same decision.
+// reference: cpd_als_iterate src/cpd.c:271-387 / mpi_cpd_als_iterate src/mpi/mpi_cpd.c:627-804
+int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
+                              double const * options, splatt_kruskal * factored) {
+  if (!h || !tensors || !options || !factored) return SPLATT_ERROR_BADINPUT;
+  const int k = h->k, N = h->N, R = h->R, ldm = h->ldm;
+  if (R > 128) {
+    fprintf(stderr, "SPLATT: multi-GPU CPD-ALS supports rank <= 128\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const int verbosity = (int)options[SPLATT_OPTION_VERBOSITY];
+  double * mats[SPB200_MAXN] = {nullptr};
+  double * lambda = static_cast<double *>(malloc(sizeof(double) * R));
+  bool ok = lambda != nullptr;
+  for (int m = 0; m < N && ok; ++m) {
+    mats[m] = static_cast<double *>(malloc(sizeof(double) * h->dims[m] * R));
+    ok = mats[m] != nullptr;
+    if (ok) for (uint64_t x = 0; x < h->dims[m] * (uint64_t)R; ++x) mats[m][x] = spb200_cpd_rand_val();
+  }
+  auto fail = [&](int rc) {
+    for (int m = 0; m < N; ++m) free(mats[m]);
+    free(lambda);
+    cudaSetDevice(h->prev_dev);
+    return rc;
+  };
+  if (!ok) return fail(SPLATT_ERROR_NOMEMORY);
+  int rc = SPLATT_SUCCESS;
+  for (int i = 0; i < k && rc == SPLATT_SUCCESS; ++i) {
+    DevState & s = h->d[i];
+    if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+    for (int m = 0; m < N; ++m) {
+      cudaError_t e = (ldm == R)
+          ? cudaMemcpyAsync(s.mats[m], mats[m], h->dims[m] * (size_t)R * 8, cudaMemcpyHostToDevice, s.stream)
+          : cudaMemcpy2DAsync(s.mats[m], (size_t)ldm * 8, mats[m], (size_t)R * 8, (size_t)R * 8,
+                              h->dims[m], cudaMemcpyHostToDevice, s.stream);
+      if (e != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+    }
+    if (!s.tail) rc = splatt_b200_als_tail_create(N, R, ldm, s.stream, &s.tail);
+    for (int m = 0; m < N && rc == SPLATT_SUCCESS; ++m)
+      rc = splatt_b200_als_tail_gram(s.tail, m, s.mats[m], h->dims[m]);
+  }
+  if (rc != SPLATT_SUCCESS) return fail(rc);
+
+  const double ttnormsq = spb200_csf_frobsq(tensors);
+  const uint64_t niters = (uint64_t)options[SPLATT_OPTION_NITER];
+  double fit = 0, oldfit = 0;
+  for (uint64_t it = 0; it < niters; ++it) {
+    auto t0 = std::chrono::steady_clock::now();
+    for (int m = 0; m < N; ++m) {
+      rc = multi_mttkrp_enqueue(h, m);
+      if (rc != SPLATT_SUCCESS) return fail(rc);
+      for (int i = 0; i < k; ++i) {
+        DevState & s = h->d[i];
+        if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        rc = splatt_b200_als_tail_update(s.tail, m, s.out[m], s.mats[m], h->dims[m], it == 0 ? 1 : 0);
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+        if (!(m == N - 1 && i == 0)) {          // device 0 still needs the last M1 for the fit
+          rc = multi_release(h, i, m);
+          if (rc != SPLATT_SUCCESS) return fail(rc);
+        }
+      }
+    }
+    if (cudaSetDevice(h->d[0].dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+    rc = splatt_b200_als_tail_fit(h->d[0].tail, h->d[0].mats[N - 1], h->d[0].out[N - 1],
+                                  h->dims[N - 1], ttnormsq, &fit, lambda);
+    if (rc != SPLATT_SUCCESS) return fail(rc);
+    rc = multi_release(h, 0, N - 1);
+    if (rc != SPLATT_SUCCESS) return fail(rc);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (verbosity > SPLATT_VERBOSITY_NONE)
+      printf("  its = %3llu (%0.3fs)  fit = %0.5f  delta = %+0.4e\n", (unsigned long long)it + 1,
+             secs, fit, fit - oldfit);
+    if (fit == 1. || (it > 0 && std::fabs(fit - oldfit) < options[SPLATT_OPTION_TOLERANCE])) break;
+    oldfit = fit;
+  }
+  // factors back from device 0 (replicas agree to rounding)
+  {
+    DevState & s = h->d[0];
+    if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+    for (int m = 0; m < N; ++m) {
+      cudaError_t e = (ldm == R)
+          ? cudaMemcpyAsync(mats[m], s.mats[m], h->dims[m] * (size_t)R * 8, cudaMemcpyDeviceToHost, s.stream)
+          : cudaMemcpy2DAsync(mats[m], (size_t)R * 8, s.mats[m], (size_t)ldm * 8, (size_t)R * 8,
+                              h->dims[m], cudaMemcpyDeviceToHost, s.stream);
+      if (e != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+    }
+  }
+  for (int i = 0; i < k; ++i) {
+    cudaSetDevice(h->d[i].dev);
+    if (cudaStreamSynchronize(h->d[i].stream) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+  }
+  cudaSetDevice(h->prev_dev);
+  spb200_cpd_postprocess(mats, h->dims, N, R, lambda);
+  factored->fit = fit;
+  factored->rank = (splatt_idx_t)R;
+  factored->nmodes = (splatt_idx_t)N;
+  factored->lambda = lambda;
+  for (int m = 0; m < N; ++m) {
+    factored->dims[m] = h->dims[m];
+    factored->factors[m] = mats[m];
+  }
+  return SPLATT_SUCCESS;
+}
+
+double splatt_b200_multi_last_ms(splatt_b200_multi const * h) { return h ? h->last_ms : 0.0; }
+
+}  // extern "C"

@@ -335,6 +335,7 @@ void spb200_free_stream(FiberStream * s) {
   for (int l = 0; l < SPB200_MAXN; ++l)
     if (s->up[l]) cudaFree(s->up[l]);
   if (s->desc) cudaFree(s->desc);
+  if (s->anc) cudaFree(s->anc);
   *s = FiberStream();
 }
 
@@ -440,8 +441,149 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
                                       sc.sidx[N - 2].as<uint32_t>(), sc.dl.as<uint8_t>(), N, nrec, 0,
                                       nrec, out->rec);
   }
+  if (N >= 4) {
+    // level-(N-3) index of every record, beside the records (root kernels of deep trees);
+    // padded so 16-byte TMA copies of a range tail stay inside the allocation
+    const size_t ab = (std::max<uint64_t>(nrec, 1) * 4 + 15) & ~(size_t)15;
+    void * anc = nullptr;
+    if (cudaMalloc(&anc, ab) != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+    out->anc = static_cast<uint32_t *>(anc);
+    cudaMemset(anc, 0, ab);
+    if (nrec)
+      CK(cudaMemcpy(anc, sc.sidx[N - 3].as<uint32_t>(), nrec * 4, cudaMemcpyDeviceToDevice));
+    held += ab;
+  }
   held += desc.bytes;
   out->desc = static_cast<uint32_t *>(desc.release());
+  out->bytes = held;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return SPLATT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// Slicing a whole stream into shards (multi-GPU from one build).
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void k_rebase_desc(uint32_t * __restrict__ desc, uint64_t nchunks, int stride,
+                              const uint32_t * __restrict__ base) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < nchunks * (uint64_t)stride) desc[i] -= base[i % stride];
+}
+__global__ void k_count_fibers(const SpRec * __restrict__ rec, uint64_t n,
+                               unsigned long long * __restrict__ count) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  unsigned c = 0;
+  if (i < n) c = ((rec[i].aux >> SPB200_IDX_BITS) != 0u) || (i + 1 == n);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+}  // namespace
+
+int spb200_slice_stream(const FiberStream & w, int src_dev, uint64_t c0, uint64_t c1, int dst_dev,
+                        FiberStream * out) {
+  *out = FiberStream();
+  if (w.ktile_rows || w.nrec != w.nrec_total) {
+    fprintf(stderr, "SPLATT: only whole, untiled streams can be sliced\n");
+    return SPLATT_ERROR_BADINPUT;
+  }
+  const int N = w.nmodes;
+  const int stride = N - 2;
+  if (c1 > w.nchunks) c1 = w.nchunks;
+  if (c0 > c1) c0 = c1;
+  const uint64_t r0 = c0 * SPB200_CHUNK;
+  const uint64_t r1 = std::min<uint64_t>(c1 * SPB200_CHUNK, w.nrec);
+  const uint64_t nrec = r1 > r0 ? r1 - r0 : 0;
+  out->nmodes = N;
+  for (int l = 0; l < N; ++l) out->perm[l] = w.perm[l];
+  out->nrec_total = w.nrec_total;
+  out->leaf_rows = w.leaf_rows;
+  out->nrec = nrec;
+  out->nchunks = c1 - c0;
+
+  // node numbers at the cut points (from the source device)
+  uint32_t first[SPB200_MAXN] = {0}, next[SPB200_MAXN] = {0};
+  uint32_t last_aux = 0;
+  CK(cudaSetDevice(src_dev));
+  if (nrec && stride > 0) {
+    CK(cudaMemcpy(first, w.desc + c0 * stride, sizeof(uint32_t) * stride, cudaMemcpyDeviceToHost));
+    if (c1 < w.nchunks)
+      CK(cudaMemcpy(next, w.desc + c1 * stride, sizeof(uint32_t) * stride, cudaMemcpyDeviceToHost));
+  }
+  if (nrec) CK(cudaMemcpy(&last_aux, &w.rec[r1 - 1].aux, 4, cudaMemcpyDeviceToHost));
+  const uint32_t last_c = last_aux >> SPB200_IDX_BITS;
+
+  CK(cudaSetDevice(dst_dev));
+  size_t held = 0;
+  auto peer_copy = [&](void * dst, const void * src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    if (src_dev == dst_dev) return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice);
+    return cudaMemcpyPeer(dst, dst_dev, src, src_dev, bytes);
+  };
+  {
+    void * rec = nullptr;
+    if (cudaMalloc(&rec, std::max<uint64_t>(nrec, 1) * sizeof(SpRec)) != cudaSuccess)
+      return SPLATT_ERROR_NOMEMORY;
+    out->rec = static_cast<SpRec *>(rec);
+    CK(peer_copy(rec, w.rec + r0, nrec * sizeof(SpRec)));
+    held += nrec * sizeof(SpRec);
+  }
+  if (w.anc) {
+    const size_t ab = (std::max<uint64_t>(nrec, 1) * 4 + 15) & ~(size_t)15;
+    void * anc = nullptr;
+    if (cudaMalloc(&anc, ab) != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+    out->anc = static_cast<uint32_t *>(anc);
+    CK(cudaMemset(anc, 0, ab));
+    CK(peer_copy(anc, w.anc + r0, nrec * 4));
+    held += ab;
+  }
+  for (int l = 0; l <= N - 3; ++l) {
+    uint64_t nn = 0;
+    if (nrec) {
+      // node holding the shard's last record: the one before `next` if that record ends
+      // level l (close count >= N-1-l), else `next` itself continues it
+      const uint64_t lastn = (c1 < w.nchunks)
+                                 ? (uint64_t)next[l] - ((last_c >= (uint32_t)(N - 1 - l)) ? 1u : 0u)
+                                 : w.nnodes[l] - 1;
+      nn = lastn - first[l] + 1;
+    }
+    void * up = nullptr;
+    if (cudaMalloc(&up, (nn + 1) * 4) != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+    out->up[l] = static_cast<uint32_t *>(up);
+    CK(cudaMemset(up, 0, (nn + 1) * 4));
+    CK(peer_copy(up, w.up[l] + first[l], nn * 4));
+    out->nnodes[l] = nn;
+    held += (nn + 1) * 4;
+  }
+  {
+    const size_t db = std::max<uint64_t>(out->nchunks, 1) * (stride > 0 ? stride : 1) * 4;
+    void * desc = nullptr;
+    if (cudaMalloc(&desc, db) != cudaSuccess) { spb200_free_stream(out); return SPLATT_ERROR_NOMEMORY; }
+    out->desc = static_cast<uint32_t *>(desc);
+    held += db;
+    if (stride > 0 && out->nchunks) {
+      CK(peer_copy(desc, w.desc + c0 * stride, out->nchunks * stride * 4));
+      DevBuf base;
+      CK(base.alloc(sizeof(uint32_t) * stride));
+      CK(cudaMemcpy(base.p, first, sizeof(uint32_t) * stride, cudaMemcpyHostToDevice));
+      k_rebase_desc<<<nblk(out->nchunks * stride), 256>>>(out->desc, out->nchunks, stride,
+                                                          base.as<uint32_t>());
+      CK(cudaDeviceSynchronize());
+    }
+  }
+  // fibers (level N-2 nodes) intersecting the shard
+  if (N >= 2) {
+    unsigned long long nf = 0;
+    if (nrec) {
+      DevBuf cnt;
+      CK(cnt.alloc(8));
+      CK(cudaMemset(cnt.p, 0, 8));
+      k_count_fibers<<<nblk(nrec), 256>>>(out->rec, nrec, cnt.as<unsigned long long>());
+      CK(cudaMemcpy(&nf, cnt.p, 8, cudaMemcpyDeviceToHost));
+    }
+    out->nnodes[N - 2] = nf;
+  }
+  out->nnodes[N - 1] = nrec;
   out->bytes = held;
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());

@@ -473,6 +473,16 @@ int splatt_b200_gather_probe_ex(
  * gpu_launches evidence). */
 uint64_t splatt_b200_launch_count(void);
 
+/* Number of fiber streams built (sorted + scanned) in this process so far. */
+uint64_t splatt_b200_build_count(void);
+
+/* The bare splatt_mttkrp entry keeps the device mirrors it builds (LRU of
+ * SPLATT_B200_CACHE entries, default 2, 0 = rebuild on every call as the reference
+ * rebuilds its workspace, src/mttkrp.c:1796).  A mirror is reused only when the CSF array,
+ * its policy / rank / shape, the addresses of its arrays AND a content fingerprint match.
+ * Call this before freeing a CSF whose mirror should release its HBM now. */
+void splatt_b200_cache_clear(void);
+
 /* Library / build identification, e.g. "splatt_b200 0.1 sm_100a". */
 char const * splatt_b200_version(void);
 

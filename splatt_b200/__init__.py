@@ -4,8 +4,8 @@ The product is splatt_b200/libsplatt_b200.so (hand-written sm_100a CUDA, C ABI i
 include/splatt_b200.h).  This package is the thin Python host layer over it.
 """
 from . import _abi  # noqa: F401
-from .api import (Csf, MttkrpWorkspace, MultiGpu, SplattError, Tensor, cpd_als,  # noqa: F401
-                  csf_alloc, default_opts, launch_count, mttkrp)
+from .api import (Csf, MttkrpWorkspace, MultiGpu, SplattError, Tensor, build_count,  # noqa: F401
+                  cache_clear, cpd_als, csf_alloc, default_opts, launch_count, mttkrp)
 
-__all__ = ["Csf", "MttkrpWorkspace", "MultiGpu", "SplattError", "Tensor", "cpd_als", "csf_alloc",
-           "default_opts", "launch_count", "mttkrp"]
+__all__ = ["Csf", "MttkrpWorkspace", "MultiGpu", "SplattError", "Tensor", "build_count",
+           "cache_clear", "cpd_als", "csf_alloc", "default_opts", "launch_count", "mttkrp"]

@@ -102,7 +102,7 @@ EXPORTS = [
     "splatt_b200_tensor_shard", "splatt_b200_mttkrp_multicast_sync",
     "splatt_b200_multi_env_devices", "splatt_b200_multi_create", "splatt_b200_multi_free",
     "splatt_b200_multi_info", "splatt_b200_multi_mttkrp_host", "splatt_b200_multi_cpd_als",
-    "splatt_b200_multi_last_ms",
+    "splatt_b200_multi_last_ms", "splatt_b200_build_count", "splatt_b200_cache_clear",
 ]
 
 _lib = None
@@ -214,6 +214,10 @@ def load() -> C.CDLL:
                                               C.POINTER(SplattKruskal)]
     lib.splatt_b200_multi_last_ms.restype = C.c_double
     lib.splatt_b200_multi_last_ms.argtypes = [C.c_void_p]
+    lib.splatt_b200_build_count.restype = C.c_uint64
+    lib.splatt_b200_build_count.argtypes = []
+    lib.splatt_b200_cache_clear.restype = None
+    lib.splatt_b200_cache_clear.argtypes = []
     lib.splatt_b200_launch_count.restype = C.c_uint64
     lib.splatt_b200_launch_count.argtypes = []
     lib.splatt_b200_version.restype = C.c_char_p

@@ -338,6 +338,16 @@ def launch_count() -> int:
     return int(A.load().splatt_b200_launch_count())
 
 
+def build_count() -> int:
+    """Fiber streams built (sort + scans) in this process so far."""
+    return int(A.load().splatt_b200_build_count())
+
+
+def cache_clear() -> None:
+    """Drop the device mirrors kept by the bare splatt_mttkrp entry point."""
+    A.load().splatt_b200_cache_clear()
+
+
 class MultiGpu:
     """Single-process multi-GPU engine (splatt_b200_multi): one host process, several
     devices, the exchange fused into the MTTKRP kernel over NVLink multicast (or the

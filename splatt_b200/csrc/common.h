@@ -111,6 +111,7 @@ struct MttkrpArgs {
   int              outdepth;  // level of the output mode
   int              ktiled;    // stream is leaf-tile ordered: keep non-leaf gathers out of L1
   int              multicast; // `out` is an NVLink multicast address: reduce with multimem.red
+  int              rpad, apad; // shared-memory stagger: pad records / pad ids per group region (0 = none)
   // Group barrier folded into the kernel's tail (multicast launches only; null = off):
   // after its last row reduction every CTA fences at system scope; the last CTA to finish
   // adds 1 to the group's flag on EVERY GPU (multimem.red on sync_mc) and spins on this
@@ -171,6 +172,7 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth,
                          uint64_t out_rows, cudaStream_t stream, bool multicast_out = false,
                          int col_begin = 0, int col_count = 0, const GroupSync * sync = nullptr);
 extern unsigned long long g_spb200_launches;
+extern unsigned long long g_spb200_builds;     // fiber streams built (sort + scans) so far
 inline void spb200_count_launches(unsigned n) { __atomic_fetch_add(&g_spb200_launches, n, __ATOMIC_RELAXED); }
 
 // mttkrp_tiled.cu -- 3-mode root kernel with the leaf factor staged tile by tile in smem

@@ -290,8 +290,8 @@ __global__ void k_gram(const double * __restrict__ A, unsigned long long I, int 
 // the pseudo-inverse (the role of the GELSS fallback :566-603).
 __global__ void k_form_chol(const double * __restrict__ ata, int nmodes, int mode, int R,
                             double * __restrict__ Lout, double * __restrict__ Pout,
-                            int * __restrict__ info) {
-  extern __shared__ double sm[];             // R*R working copy (+ R*R for the fallback)
+                            double * __restrict__ Vscratch, int * __restrict__ info) {
+  extern __shared__ double sm[];             // R*R working copy (the fallback's V is in global)
   double * a = sm;
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
@@ -332,7 +332,7 @@ __global__ void k_form_chol(const double * __restrict__ ata, int nmodes, int mod
   // not SPD: Jacobi eigen-decomposition -> pseudo-inverse (one thread; rare path)
   if (threadIdx.x == 0) {
     double * A2 = a;            // reuse as the working symmetric matrix
-    double * V  = sm + R * R;
+    double * V  = Vscratch;
     for (int x = 0; x < R * R; ++x) { A2[x] = Pout[x]; V[x] = 0.0; }
     for (int i = 0; i < R; ++i) V[i + i * R] = 1.0;
     for (int sweep = 0; sweep < 64; ++sweep) {
@@ -481,8 +481,11 @@ struct DevTail {
   double * lambda = nullptr;  // R
   double * inner = nullptr;   // 1
   int *    info = nullptr;
+  double * jac_v = nullptr;   // R x R scratch of the pseudo-inverse fallback
   double * h_back = nullptr;  // pinned: N*R*R + R + 1 (+1 info)
   cudaStream_t s = nullptr;
+  int      solve_threads = 128;   // rows per block of k_solve_rows (shared memory permitting)
+  bool     failed = false;        // a launch was rejected: results are not to be trusted
 
   bool alloc(int N_, int R_, int ld_, cudaStream_t st) {
     N = N_; R = R_; ld = ld_; s = st;
@@ -493,18 +496,35 @@ struct DevTail {
               cudaMalloc(&lambda, sizeof(double) * R) == cudaSuccess &&
               cudaMalloc(&inner, sizeof(double)) == cudaSuccess &&
               cudaMalloc(&info, sizeof(int) * 2) == cudaSuccess &&
+              cudaMalloc(&jac_v, sizeof(double) * R * R) == cudaSuccess &&
               cudaMallocHost(&h_back, sizeof(double) * ((size_t)N * R * R + R + 2)) == cudaSuccess;
     if (ok) {
-      cudaFuncSetAttribute(k_form_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * R * R * 8);
-      cudaFuncSetAttribute(k_solve_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (R * R + R * 128) * 8);
-      cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * R * 8);
+      // shared-memory budgets: k_form_chol R*R doubles (128 KB at R = 128); k_solve_rows
+      // R*R + R*threads doubles -- shrink its row tile until it fits the opt-in limit
+      int dev = 0, lim = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      solve_threads = 128;
+      while (solve_threads > 32 && (size_t)(R * R + R * solve_threads) * 8 > (size_t)lim) solve_threads /= 2;
+      ok = (size_t)(R * R + R * solve_threads) * 8 <= (size_t)lim && (size_t)R * R * 8 <= (size_t)lim &&
+           cudaFuncSetAttribute(k_form_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, R * R * 8) == cudaSuccess &&
+           cudaFuncSetAttribute(k_solve_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (R * R + R * solve_threads) * 8) == cudaSuccess &&
+           cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * R * 8) == cudaSuccess;
+      if (!ok) fprintf(stderr, "SPLATT: rank %d does not fit the device ALS tail (shared memory)\n", R);
     }
     return ok;
   }
+  void check(const char * what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      fprintf(stderr, "SPLATT: ALS tail launch '%s' failed: %s\n", what, cudaGetErrorString(e));
+      failed = true;
+    }
+  }
   void release() {
     cudaFree(ata); cudaFree(chol); cudaFree(pinv); cudaFree(lam_acc); cudaFree(lambda);
-    cudaFree(inner); cudaFree(info);
+    cudaFree(inner); cudaFree(info); cudaFree(jac_v);
     if (h_back) cudaFreeHost(h_back);
   }
   void gram(const double * A, uint64_t I, int m) {
@@ -512,18 +532,23 @@ struct DevTail {
     cudaMemsetAsync(G, 0, sizeof(double) * R * R, s);
     const unsigned blocks = (unsigned)std::min<uint64_t>((I + 31) / 32, 592);
     k_gram<<<blocks, 256, 32 * R * 8, s>>>(A, I, R, ld, G);
+    check("k_gram");
     spb200_count_launches(1);
   }
   // one mode step after the MTTKRP: d_out (M1) -> d_mat (new factor), lambda, Gram
   void mode_step(const double * d_out, double * d_mat, uint64_t I, int m, bool two_norm) {
-    k_form_chol<<<1, 256, 2 * R * R * 8, s>>>(ata, N, m, R, chol, pinv, info);
-    k_solve_rows<<<(unsigned)((I + 127) / 128), 128, (R * R + R * 128) * 8, s>>>(
+    k_form_chol<<<1, 256, R * R * 8, s>>>(ata, N, m, R, chol, pinv, jac_v, info);
+    check("k_form_chol");
+    const int T = solve_threads;
+    k_solve_rows<<<(unsigned)((I + T - 1) / T), T, (R * R + R * T) * 8, s>>>(
         d_out, d_mat, I, R, ld, chol, pinv, info);
+    check("k_solve_rows");
     cudaMemsetAsync(lam_acc, 0, sizeof(double) * R, s);
     dim3 g((unsigned)std::min<uint64_t>((I + 7) / 8, 1184), (R + 31) / 32);
     k_colnorm<<<g, 256, 0, s>>>(d_mat, I, R, ld, two_norm ? 1 : 0, lam_acc);
     k_finish_lambda<<<(R + 127) / 128, 128, 0, s>>>(lam_acc, R, two_norm ? 1 : 0, lambda);
     k_scale_cols<<<(unsigned)((I * R + 255) / 256), 256, 0, s>>>(d_mat, I, R, ld, lambda);
+    check("normalise");
     spb200_count_launches(5);
     gram(d_mat, I, m);
   }
@@ -610,6 +635,8 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
   ok = ok && cudaMalloc(&d_out, maxdim * (size_t)ldm * 8) == cudaSuccess;
   if (host_tail) ok = ok && cudaMallocHost(&m1, maxdim * (size_t)R * 8) == cudaSuccess;
   else ok = ok && tail.alloc(N, R, ldm, stream);
+  if (ok && !host_tail && verbosity > SPLATT_VERBOSITY_LOW)
+    printf("SPLATT-B200: device ALS tail, %d rows per solve block\n", tail.solve_threads);
 
   double fit = 0, oldfit = 0;
   const double ttnormsq = csf_frobsq(tensors);
@@ -679,7 +706,7 @@ int splatt_cpd_als(splatt_csf const * const tensors, splatt_idx_t const nfactors
       cudaMemcpyAsync(tail.h_back + nb, tail.lambda, R * 8, cudaMemcpyDeviceToHost, stream);
       cudaMemcpyAsync(tail.h_back + nb + R, tail.inner, 8, cudaMemcpyDeviceToHost, stream);
       cudaMemcpyAsync(tail.h_back + nb + R + 1, tail.info, 4, cudaMemcpyDeviceToHost, stream);
-      if (cudaStreamSynchronize(stream) != cudaSuccess) { ok = false; break; }
+      if (cudaStreamSynchronize(stream) != cudaSuccess || tail.failed) { ok = false; break; }
       for (int m = 0; m < N; ++m)
         memcpy(ata[m].data(), tail.h_back + (size_t)m * R * R, sizeof(double) * R * R);
       memcpy(lambda, tail.h_back + nb, sizeof(double) * R);
@@ -754,7 +781,7 @@ int splatt_b200_als_tail_gram(splatt_b200_als_tail * h, int mode, double const *
                               uint64_t rows) {
   if (!h || mode < 0 || mode >= h->t.N) return SPLATT_ERROR_BADINPUT;
   h->t.gram(d_factor, rows, mode);
-  return cudaGetLastError() == cudaSuccess ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+  return (cudaGetLastError() == cudaSuccess && !h->t.failed) ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
 }
 
 // One mode update: d_m1 (the summed MTTKRP result) -> d_factor, lambda, Gram of the mode.
@@ -762,7 +789,7 @@ int splatt_b200_als_tail_update(splatt_b200_als_tail * h, int mode, double const
                                 double * d_factor, uint64_t rows, int first_iteration) {
   if (!h || mode < 0 || mode >= h->t.N) return SPLATT_ERROR_BADINPUT;
   h->t.mode_step(d_m1, d_factor, rows, mode, first_iteration != 0);
-  return cudaGetLastError() == cudaSuccess ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+  return (cudaGetLastError() == cudaSuccess && !h->t.failed) ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
 }
 
 // Fit after the last mode's update (reference: p_calc_fit src/cpd.c:237-265).  Synchronises
@@ -780,7 +807,7 @@ int splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_fac
   cudaMemcpyAsync(t.h_back, t.ata, nb * 8, cudaMemcpyDeviceToHost, t.s);
   cudaMemcpyAsync(t.h_back + nb, t.lambda, R * 8, cudaMemcpyDeviceToHost, t.s);
   cudaMemcpyAsync(t.h_back + nb + R, t.inner, 8, cudaMemcpyDeviceToHost, t.s);
-  if (cudaStreamSynchronize(t.s) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+  if (cudaStreamSynchronize(t.s) != cudaSuccess || t.failed) return SPLATT_ERROR_BADINPUT;
   std::vector<std::vector<double>> ata(N, std::vector<double>((size_t)R * R));
   for (int m = 0; m < N; ++m)
     memcpy(ata[m].data(), t.h_back + (size_t)m * R * R, sizeof(double) * R * R);

@@ -7,6 +7,8 @@
 #include <ctime>
 #include <chrono>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -238,9 +240,84 @@ cudaError_t pipelined_call(WsPriv * w, splatt_b200_matrix_t ** mats, int mode, u
   return e;
 }
 
+// ---------------------------------------------------------------------------
+// Device-mirror cache of the bare splatt_mttkrp entry point.  The reference pays an
+// O(nslices) workspace build per call (src/mttkrp.c:1796); a per-call device mirror would
+// cost the CSF expansion, the upload of the whole tensor and one radix sort per stream.  So
+// workspaces built by splatt_mttkrp are kept (LRU, SPLATT_B200_CACHE entries, default 2,
+// 0 = off) and found again by (tensors, policy, rank, shape, array addresses) plus a content
+// fingerprint of the first CSF -- a tensor freed and another one allocated at the same
+// addresses does not match.  matlab/splatt_mttkrp.c:47-68 is the caller this serves.
+// ---------------------------------------------------------------------------
+struct MirrorKey {
+  const void * tensors;
+  const void * pt0;
+  const void * vals0;
+  uint64_t nnz, fingerprint;
+  uint64_t dims[SPB200_MAXN];
+  int nmodes, csf_alloc, ncolumns, layout, ndev, devs[16];
+  bool operator==(const MirrorKey & o) const { return memcmp(this, &o, sizeof(MirrorKey)) == 0; }
+};
+struct MirrorEntry { MirrorKey key; splatt_mttkrp_ws * ws; uint64_t stamp; };
+std::mutex g_mirror_mu;
+std::vector<MirrorEntry> g_mirror;
+uint64_t g_mirror_stamp = 0;
+
+int mirror_cap() {
+  const char * e = getenv("SPLATT_B200_CACHE");
+  const int v = e ? atoi(e) : 2;
+  return v < 0 ? 0 : (v > 64 ? 64 : v);
+}
+
+uint64_t fnv(uint64_t h, const void * p, size_t n) {
+  const unsigned char * b = static_cast<const unsigned char *>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+MirrorKey mirror_key(const splatt_csf * tensors, int csf_alloc, int ncolumns) {
+  MirrorKey k;
+  memset(&k, 0, sizeof(k));
+  const splatt_csf & t = tensors[0];
+  const int N = (int)t.nmodes;
+  k.tensors = tensors;
+  k.pt0 = t.pt;
+  k.vals0 = t.pt ? t.pt[0].vals : nullptr;
+  k.nnz = t.nnz;
+  k.nmodes = N;
+  k.csf_alloc = csf_alloc;
+  k.ncolumns = ncolumns;
+  k.layout = layout_from_env();
+  for (int m = 0; m < N; ++m) k.dims[m] = t.dims[m];
+  k.ndev = splatt_b200_multi_env_devices(k.devs, 16);
+  // content fingerprint: shape of the tree + strided samples of values and leaf indices
+  uint64_t h = 1469598103934665603ull;
+  h = fnv(h, &t.ntiles, sizeof(t.ntiles));
+  h = fnv(h, t.dim_perm, sizeof(t.dim_perm[0]) * N);
+  for (uint64_t tile = 0; tile < t.ntiles && tile < 64; ++tile) {
+    const csf_sparsity & pt = t.pt[tile];
+    h = fnv(h, pt.nfibs, sizeof(pt.nfibs[0]) * N);
+    const uint64_t n = pt.vals ? pt.nfibs[N - 1] : 0;
+    const uint64_t step = n > 2048 ? n / 2048 : 1;
+    for (uint64_t i = 0; i < n; i += step) {
+      h = fnv(h, &pt.vals[i], sizeof(double));
+      if (pt.fids[N - 1]) h = fnv(h, &pt.fids[N - 1][i], sizeof(splatt_idx_t));
+    }
+    if (n) h = fnv(h, &pt.vals[n - 1], sizeof(double));
+  }
+  k.fingerprint = h;
+  return k;
+}
+
 }  // namespace
 
 extern "C" {
+
+void splatt_b200_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_mirror_mu);
+  for (auto & e : g_mirror) splatt_mttkrp_free_ws(e.ws);
+  g_mirror.clear();
+}
 
 splatt_mttkrp_ws * splatt_mttkrp_alloc_ws(splatt_csf const * const tensors,
                                           splatt_idx_t const ncolumns,
@@ -423,8 +500,31 @@ int splatt_mttkrp(splatt_idx_t const mode, splatt_idx_t const ncolumns,
     return SPLATT_ERROR_BADINPUT;
   }
   const int N = (int)tensors[0].nmodes;
-  splatt_mttkrp_ws * ws = splatt_mttkrp_alloc_ws(tensors, ncolumns, options);
-  if (!ws) return SPLATT_ERROR_NOMEMORY;
+  // the device mirror of a tensor seen before is reused (see MirrorKey above)
+  const int cap = mirror_cap();
+  std::unique_lock<std::mutex> lk(g_mirror_mu, std::defer_lock);
+  splatt_mttkrp_ws * ws = nullptr;
+  if (cap > 0) {
+    lk.lock();                       // also serialises calls that share a cached workspace
+    const MirrorKey key = mirror_key(tensors, (int)options[SPLATT_OPTION_CSF_ALLOC], (int)ncolumns);
+    for (auto & e : g_mirror)
+      if (e.key == key) { ws = e.ws; e.stamp = ++g_mirror_stamp; break; }
+    if (!ws) {
+      ws = splatt_mttkrp_alloc_ws(tensors, ncolumns, options);
+      if (!ws) return SPLATT_ERROR_NOMEMORY;
+      if ((int)g_mirror.size() >= cap) {
+        size_t lru = 0;
+        for (size_t i = 1; i < g_mirror.size(); ++i)
+          if (g_mirror[i].stamp < g_mirror[lru].stamp) lru = i;
+        splatt_mttkrp_free_ws(g_mirror[lru].ws);
+        g_mirror.erase(g_mirror.begin() + lru);
+      }
+      g_mirror.push_back(MirrorEntry{key, ws, ++g_mirror_stamp});
+    }
+  } else {
+    ws = splatt_mttkrp_alloc_ws(tensors, ncolumns, options);
+    if (!ws) return SPLATT_ERROR_NOMEMORY;
+  }
   // same wrapping as the reference (src/mttkrp.c:1773-1786)
   splatt_b200_matrix_t store[SPLATT_B200_MAX_NMODES + 1];
   splatt_b200_matrix_t * mats[SPLATT_B200_MAX_NMODES + 1] = {nullptr};
@@ -441,7 +541,7 @@ int splatt_mttkrp(splatt_idx_t const mode, splatt_idx_t const ncolumns,
   store[SPLATT_B200_MAX_NMODES].vals = matout;
   mats[SPLATT_B200_MAX_NMODES] = &store[SPLATT_B200_MAX_NMODES];
   splatt_mttkrp_csf(tensors, mats, mode, nullptr, ws, options);
-  splatt_mttkrp_free_ws(ws);
+  if (cap == 0) splatt_mttkrp_free_ws(ws);
   return SPLATT_SUCCESS;
 }
 

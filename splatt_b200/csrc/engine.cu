@@ -180,12 +180,6 @@ int csf_to_coo(const splatt_csf * ct, std::vector<uint32_t> * ind, std::vector<d
   return SPLATT_SUCCESS;
 }
 
-int use_device(int device, int * prev) {
-  SPB200_CUDA_OK(cudaGetDevice(prev));
-  if (device >= 0 && device != *prev) SPB200_CUDA_OK(cudaSetDevice(device));
-  return SPLATT_SUCCESS;
-}
-
 struct PermSpec { int perm[SPB200_MAXN]; bool presorted; };
 
 int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
@@ -198,7 +192,7 @@ int build_tensor(int N, const uint64_t * dims, const DevCoo & dc,
   T->layout = bo.layout;
   T->shard_rank = bo.shard_rank;
   T->shard_count = bo.shard_count > 1 ? bo.shard_count : 1;
-  SPB200_CUDA_OK(cudaGetDevice(&T->device));
+  if (cudaGetDevice(&T->device) != cudaSuccess) { delete T; return SPLATT_ERROR_BADINPUT; }
   T->streams.resize(stream_perms.size());
   int num_sms = 148;
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, T->device);
@@ -292,9 +286,11 @@ int splatt_b200_tensor_from_coo(int nmodes, uint64_t const * dims, uint64_t nnz,
   memset(&bo, 0, sizeof(bo));
   bo.device = -1;
   if (bopts) bo = *bopts;
-  int prev = 0;
-  int rc = use_device(bo.device, &prev);
-  if (rc != SPLATT_SUCCESS) return rc;
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+  DeviceGuard guard(bo.device >= 0 ? bo.device : cur);     // restored on every return path
+  if (!guard.ok) return SPLATT_ERROR_BADINPUT;
+  int rc = SPLATT_SUCCESS;
 
   const int N = nmodes;
   std::vector<PermSpec> sp;
@@ -330,7 +326,6 @@ int splatt_b200_tensor_from_coo(int nmodes, uint64_t const * dims, uint64_t nnz,
   DevCoo dc;
   rc = upload_coo(N, nnz, ind, vals, on_device, &dc);
   if (rc == SPLATT_SUCCESS) rc = build_tensor(N, dims, dc, sp, plan, bo, out);
-  if (bo.device >= 0 && bo.device != prev) cudaSetDevice(prev);
   return rc;
 }
 
@@ -355,9 +350,11 @@ int splatt_b200_tensor_from_csf(splatt_csf const * tensors, int csf_alloc,
   memset(&bo, 0, sizeof(bo));
   bo.device = -1;
   if (bopts) bo = *bopts;
-  int prev = 0;
-  int rc = use_device(bo.device, &prev);
-  if (rc != SPLATT_SUCCESS) return rc;
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+  DeviceGuard guard(bo.device >= 0 ? bo.device : cur);     // restored on every return path
+  if (!guard.ok) return SPLATT_ERROR_BADINPUT;
+  int rc = SPLATT_SUCCESS;
 
   uint64_t dims[SPB200_MAXN];
   for (int m = 0; m < N; ++m) dims[m] = tensors[0].dims[m];
@@ -415,7 +412,6 @@ int splatt_b200_tensor_from_csf(splatt_csf const * tensors, int csf_alloc,
   DevCoo dc;
   rc = upload_coo(N, tensors[0].nnz, hp, vals.data(), 0, &dc);
   if (rc == SPLATT_SUCCESS) rc = build_tensor(N, dims, dc, sp, plan, bo, out);
-  if (bo.device >= 0 && bo.device != prev) cudaSetDevice(prev);
   return rc;
 }
 
@@ -555,6 +551,7 @@ int splatt_b200_mttkrp_multicast_sync(splatt_b200_tensor const * t, int mode, in
     splatt_b200_tensor * tm = const_cast<splatt_b200_tensor *>(t);
     SPB200_CUDA_OK(cudaMalloc(&tm->cta_done, 64));
     SPB200_CUDA_OK(cudaMemset(tm->cta_done, 0, 64));
+    SPB200_CUDA_OK(cudaDeviceSynchronize());   // callers' streams do not synchronise with the null stream
   }
   GroupSync gs;
   gs.mc_flag = sync->mc_flag; gs.local_flag = sync->local_flag; gs.cta_done = t->cta_done;
@@ -643,6 +640,7 @@ void splatt_b200_shard_range(uint64_t nnz, int rank, int count_shards, uint64_t 
 }
 
 uint64_t splatt_b200_launch_count(void) { return g_spb200_launches; }
+uint64_t splatt_b200_build_count(void) { return g_spb200_builds; }
 
 char const * splatt_b200_version(void) { return "splatt_b200 0.1 (sm_100a fiber-stream MTTKRP)"; }
 

@@ -19,13 +19,15 @@ static int launch_variant(const MttkrpArgs & args, int num_sms, cudaStream_t str
     else return mttkrp_stream_kernel<N, L, KIND, BATCH, KT, MC, MINB, STAGES>;
   }();
   static_assert(MINB != 0 || STAGES == kStages, "a non-default ring depth needs an explicit MINB");
-  constexpr size_t smem = smem_bytes(STAGES, KIND == SPB200_KIND_ROOT && N >= 4);
-  // function attributes and occupancy are per DEVICE: cache them per ordinal
+  const size_t smem = smem_bytes(STAGES, KIND == SPB200_KIND_ROOT && N >= 4, 32 / L, args.rpad, args.apad);
+  // function attributes and occupancy are per DEVICE (and per stagger setting): cache them
   static int occ_of[64] = {0};
+  static size_t smem_of[64] = {0};
   int dev = 0;
   SPB200_CUDA_OK(cudaGetDevice(&dev));
   const int slot = (dev >= 0 && dev < 64) ? dev : 0;
-  if (occ_of[slot] == 0 || dev != slot) {
+  if (occ_of[slot] == 0 || dev != slot || smem_of[slot] != smem) {
+    smem_of[slot] = smem;
     SPB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     int o = 0;

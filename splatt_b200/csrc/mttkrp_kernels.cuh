@@ -37,25 +37,25 @@ constexpr int kWarps     = kThreads / 32;
 constexpr int kStageRecs = 128;   // records per warp per stage (2 KB)
 constexpr int kStages    = 3;     // default ring depth (a template parameter of the kernel)
 
-// Shared-memory layout.  Every lane group owns one region per stage; the regions of the
-// groups of a warp are staggered by 16 bytes (one pad record / four pad ids per region), so
-// that the per-group broadcast reads of one warp instruction (LDS.128 of G different
-// records, LDS.32 of G different ids) fall into different banks.  Without the stagger the
-// regions are a multiple of 128 bytes apart and every such read is a G-way bank conflict
-// (measured: 1.0 / 1.4 shared-memory wavefronts per record for 3 / 4 modes instead of
-// 0.5 / 0.35 -- 20 % / 38 % of the L1 data-pipe load of the kernel).
-constexpr int kRecPad = 8;        // pad records per warp-stage (>= groups per warp)
-constexpr int kAncPad = 32;       // pad ids per warp-stage (4 per group)
-__host__ __device__ constexpr size_t smem_rec_bytes(int stages) {
-  return sizeof(SpRec) * kWarps * stages * (kStageRecs + kRecPad);
+// Shared-memory layout.  Every lane group owns one region per stage.  With a stagger
+// (MttkrpArgs::rpad / apad) the regions of the groups of a warp are 16 bytes further apart
+// (one pad record / four pad ids per region), so that the per-group broadcast reads of one
+// warp instruction (LDS.128 of G different records, LDS.32 of G different ids) fall into
+// different banks; without it the regions are a multiple of 128 bytes apart and every such
+// read is a G-way bank conflict (measured: 1.0 / 1.4 shared-memory wavefronts per record
+// for 3 / 4 modes).  The price is a TMA destination that is only 16-byte aligned and a
+// slightly larger footprint (which can cost an L1 carve-out step): measured, see DESIGN.md.
+__host__ __device__ constexpr size_t smem_rec_bytes(int stages, int G, int rpad) {
+  return sizeof(SpRec) * kWarps * stages * (kStageRecs + G * rpad);
 }
 __host__ __device__ constexpr size_t smem_bar_bytes(int stages) { return sizeof(uint64_t) * kWarps * stages; }
 // N >= 4 root kernels also stage the per-record level-(N-3) ancestor ids (4 B each)
-__host__ __device__ constexpr size_t smem_anc_bytes(int stages) {
-  return sizeof(uint32_t) * kWarps * stages * (kStageRecs + kAncPad);
+__host__ __device__ constexpr size_t smem_anc_bytes(int stages, int G, int apad) {
+  return sizeof(uint32_t) * kWarps * stages * (kStageRecs + G * apad);
 }
-__host__ __device__ constexpr size_t smem_bytes(int stages, bool anc) {
-  return smem_rec_bytes(stages) + smem_bar_bytes(stages) + (anc ? smem_anc_bytes(stages) : 0);
+__host__ __device__ constexpr size_t smem_bytes(int stages, bool anc, int G, int rpad, int apad) {
+  return smem_rec_bytes(stages, G, rpad) + smem_bar_bytes(stages) +
+         (anc ? smem_anc_bytes(stages, G, apad) : 0);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) {
@@ -184,18 +184,18 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
   static_assert(N >= 2 && N <= SPB200_MAXN, "2..8 modes");
   constexpr int G  = 32 / L;            // groups per warp
   constexpr int SU = kStageRecs / G;    // records per group per stage
-  constexpr int RS = SU + 1;            // region stride in records (16-byte stagger)
-  constexpr int AS = SU + 4;            // region stride in ancestor ids (16-byte stagger)
   constexpr int kStages = STAGES;       // shadows the namespace default inside the kernel
+  const int RS = SU + a.rpad;           // region stride in records (rpad = 1: 16-byte stagger)
+  const int AS = SU + a.apad;           // region stride in ancestor ids (apad = 4: 16-byte stagger)
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpRec *    srec = reinterpret_cast<SpRec *>(smem_raw);
-  uint64_t * bars = reinterpret_cast<uint64_t *>(smem_raw + smem_rec_bytes(STAGES));
+  uint64_t * bars = reinterpret_cast<uint64_t *>(smem_raw + smem_rec_bytes(STAGES, G, a.rpad));
   // level-(N-3) ancestor id of every record, staged beside the records (root, N >= 4): all
   // three row gathers of a record then depend on shared memory only -- no id -> row chain
   constexpr bool kAnc = (KIND == SPB200_KIND_ROOT && N >= 4);
   uint32_t * sanc =
-      reinterpret_cast<uint32_t *>(smem_raw + smem_rec_bytes(STAGES) + smem_bar_bytes(STAGES));
+      reinterpret_cast<uint32_t *>(smem_raw + smem_rec_bytes(STAGES, G, a.rpad) + smem_bar_bytes(STAGES));
 
   const int      warp   = threadIdx.x >> 5;
   const int      lane   = threadIdx.x & 31;

@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 unsigned long long g_spb200_launches = 0;
+unsigned long long g_spb200_builds = 0;
 
 // Tuning knob (experiments): records per gather batch of the root kernel.
 int spb200_root_batch() {
@@ -121,6 +122,11 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   for (int l = 0; l < SPB200_MAXN; ++l) a.mats[l] = (l < N) ? d_mats_by_mode[s.perm[l]] : nullptr;
   a.out      = d_out;
   a.nrec     = s.nrec;
+  if (s.nchunks > 0xffffffffull) {
+    fprintf(stderr, "SPLATT: stream too long for one launch (%llu chunks)\n",
+            (unsigned long long)s.nchunks);
+    return SPLATT_ERROR_BADINPUT;
+  }
   a.nchunks  = static_cast<unsigned int>(s.nchunks);
   a.ldm      = ldm;
   a.outdepth = outdepth;
@@ -128,6 +134,17 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   a.multicast = multicast_out ? 1 : 0;
   a.sync_mc = a.sync_local = a.sync_cta = nullptr;
   a.sync_target = 0;
+  {
+    // SPLATT_B200_STAGGER: 0 = aligned regions (bank conflicts on the broadcast reads),
+    // 1 = stagger the record regions, 2 = records and ancestor ids
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char * e = getenv("SPLATT_B200_STAGGER");
+      stagger = e ? atoi(e) : 0;
+    }
+    a.rpad = stagger >= 1 ? 1 : 0;
+    a.apad = stagger >= 2 ? 4 : 0;
+  }
 
   const int num_sms = num_sms_of_current_device();
   for (int c0 = col_begin; c0 < col_end; c0 += 64) {

@@ -227,7 +227,8 @@ struct DevState {
   double * part = nullptr;                  // fallback: local partial, maxdim x ldm
   uint32_t * flag_local = nullptr;
   cudaEvent_t ev_k = nullptr, ev_r = nullptr;
-  splatt_b200_als_tail * tail = nullptr;
+  cudaEvent_t ev_tail = nullptr;            // device 0: the mode's new factor is ready
+  splatt_b200_als_tail * tail = nullptr;    // device 0 only (see splatt_b200_multi_cpd_als)
 };
 
 #define MCK(call)                                                                               \
@@ -287,6 +288,7 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
     MCK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     MCK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_r, cudaEventDisableTiming));
+    MCK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
     for (int m = 0; m < N; ++m) {
       MCK(cudaMalloc(&s.mats[m], h->dims[m] * (size_t)h->ldm * 8));
       MCK(cudaMemset(s.mats[m], 0, h->dims[m] * (size_t)h->ldm * 8));
@@ -306,7 +308,10 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
     char * mb = reinterpret_cast<char *>(h->mc.mc);
     h->mc_flag = reinterpret_cast<uint32_t *>(mb);
     for (int m = 0; m < N; ++m) h->mc_out[m] = reinterpret_cast<double *>(mb + h->out_off[m]);
-  } else if (h->distinct && k > 1) {
+  }
+  if (h->distinct && k > 1) {
+    // peer access: the reduce kernel of the fallback reads / writes peer buffers directly, and
+    // the CPD driver's factor hand-off (cudaMemcpyPeerAsync) then goes straight over NVLink
     for (int i = 0; i < k; ++i) {
       MCK(cudaSetDevice(h->d[i].dev));
       for (int j = 0; j < k; ++j) {
@@ -314,6 +319,7 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
         int can = 0;
         MCK(cudaDeviceCanAccessPeer(&can, h->d[i].dev, h->d[j].dev));
         if (!can) {
+          if (h->multicast) continue;            // copies fall back to staging; still correct
           fprintf(stderr, "SPLATT: devices %d and %d have no peer access\n", h->d[i].dev, h->d[j].dev);
           return SPLATT_ERROR_BADINPUT;
         }
@@ -466,6 +472,7 @@ void splatt_b200_multi_free(splatt_b200_multi * h) {
     if (s.part) cudaFree(s.part);
     if (s.ev_k) cudaEventDestroy(s.ev_k);
     if (s.ev_r) cudaEventDestroy(s.ev_r);
+    if (s.ev_tail) cudaEventDestroy(s.ev_tail);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.T) splatt_b200_tensor_free(s.T);
   }
@@ -622,9 +629,14 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
   return SPLATT_SUCCESS;
 }
 
-// CPD-ALS over all devices: per mode the fused MTTKRP + exchange, then the dense tail
-// replicated on every device (the same kernels splatt_cpd_als uses on one GPU); the fit and
-// the stop decision come from device 0 only, so every device takes the same decision.
+// CPD-ALS over all devices: per mode the fused MTTKRP + exchange on every device, then the
+// dense tail ONCE, on device 0 (the same kernels splatt_cpd_als uses on one GPU), whose new
+// factor every other device pulls over NVLink before its next MTTKRP.  The factor matrices
+// are therefore single-valued: replicated tails would agree only to rounding (their
+// atomics and the multimem.red's arrive in a different order on every GPU) and on
+// ill-conditioned problems such replicas drift apart until the shards multiply with
+// inconsistent factors (measured: 300^3, 200 K nnz, rank 32 diverges after ~10 iterations).
+// The fit and the stop decision also come from device 0, so there is one decision.
 // reference: cpd_als_iterate src/cpd.c:271-387 / mpi_cpd_als_iterate src/mpi/mpi_cpd.c:627-804
 int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
                               double const * options, splatt_kruskal * factored) {
@@ -661,9 +673,11 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
                               h->dims[m], cudaMemcpyHostToDevice, s.stream);
       if (e != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
     }
-    if (!s.tail) rc = splatt_b200_als_tail_create(N, R, ldm, s.stream, &s.tail);
-    for (int m = 0; m < N && rc == SPLATT_SUCCESS; ++m)
-      rc = splatt_b200_als_tail_gram(s.tail, m, s.mats[m], h->dims[m]);
+    if (i == 0) {
+      if (!s.tail) rc = splatt_b200_als_tail_create(N, R, ldm, s.stream, &s.tail);
+      for (int m = 0; m < N && rc == SPLATT_SUCCESS; ++m)
+        rc = splatt_b200_als_tail_gram(s.tail, m, s.mats[m], h->dims[m]);
+    }
   }
   if (rc != SPLATT_SUCCESS) return fail(rc);
 
@@ -675,15 +689,32 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     for (int m = 0; m < N; ++m) {
       rc = multi_mttkrp_enqueue(h, m);
       if (rc != SPLATT_SUCCESS) return fail(rc);
-      for (int i = 0; i < k; ++i) {
-        DevState & s = h->d[i];
-        if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
-        rc = splatt_b200_als_tail_update(s.tail, m, s.out[m], s.mats[m], h->dims[m], it == 0 ? 1 : 0);
+      // device 0: the tail; everybody else: result consumed, wait for the new factor, pull it
+      {
+        DevState & s0 = h->d[0];
+        if (cudaSetDevice(s0.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        rc = splatt_b200_als_tail_update(s0.tail, m, s0.out[m], s0.mats[m], h->dims[m], it == 0 ? 1 : 0);
         if (rc != SPLATT_SUCCESS) return fail(rc);
-        if (!(m == N - 1 && i == 0)) {          // device 0 still needs the last M1 for the fit
-          rc = multi_release(h, i, m);
+        if (cudaEventRecord(s0.ev_tail, s0.stream) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        if (m != N - 1) {                        // the last M1 is still needed for the fit
+          rc = multi_release(h, 0, m);
           if (rc != SPLATT_SUCCESS) return fail(rc);
         }
+      }
+      for (int i = 1; i < k; ++i) {
+        DevState & s = h->d[i];
+        if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        rc = multi_release(h, i, m);
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+        // device 0 overwrites this factor again only one iteration later, after N-1 more
+        // group exchanges that this device takes part in AFTER the copy below (stream order)
+        const size_t bytes = h->dims[m] * (size_t)ldm * 8;
+        cudaError_t e = cudaStreamWaitEvent(s.stream, h->d[0].ev_tail, 0);
+        if (e == cudaSuccess)
+          e = (s.dev == h->d[0].dev)
+                  ? cudaMemcpyAsync(s.mats[m], h->d[0].mats[m], bytes, cudaMemcpyDeviceToDevice, s.stream)
+                  : cudaMemcpyPeerAsync(s.mats[m], s.dev, h->d[0].mats[m], h->d[0].dev, bytes, s.stream);
+        if (e != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
       }
     }
     if (cudaSetDevice(h->d[0].dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);

@@ -344,6 +344,7 @@ int spb200_build_stream(int N, const uint64_t * dims, uint64_t nnz,
                         bool presorted, int shard_rank, int shard_count,
                         const StreamTiling & tiling, FiberStream * out) {
   *out = FiberStream();
+  __atomic_fetch_add(&g_spb200_builds, 1ull, __ATOMIC_RELAXED);
   out->nmodes = N;
   for (int l = 0; l < N; ++l) out->perm[l] = perm[l];
   out->nrec_total = nnz;

@@ -45,10 +45,17 @@ class FusedExchange:
     otherwise `mttkrp` inserts the missing barrier itself (every rank takes the same
     decision, so the extra barrier is collective).
 
+    The group barrier after the kernel is by default the kernel's own tail
+    (`splatt_b200_mttkrp_multicast_sync`: every CTA fences, the last one adds 1 to a flag on
+    every GPU through the multicast address and spins on the local copy) -- no separate
+    barrier launch, no launch-skew between the kernel and its barrier.  `kernel_barrier=False`
+    (or SPLATT_B200_KERNEL_BARRIER=0) uses the symmetric-memory barrier kernel instead.
+
     `available()` is False when the process group has no multicast support (then use
     `sharded_mttkrp`: local kernel + NCCL all-reduce)."""
 
-    def __init__(self, tensor, ncolumns, group=None):
+    def __init__(self, tensor, ncolumns, group=None, kernel_barrier=None):
+        import os
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -56,10 +63,15 @@ class FusedExchange:
         self.R = ncolumns
         self.ldm = ncolumns + (ncolumns & 1)
         self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        if kernel_barrier is None:
+            kernel_barrier = os.environ.get("SPLATT_B200_KERNEL_BARRIER", "1") != "0"
+        self.kernel_barrier = bool(kernel_barrier)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.bufs, self.hdls = [], []
         self.ok = True
         self.error = None
+        self.flags = None
         try:
             for m in range(tensor.nmodes):
                 b = symm_mem.empty((tensor.dims[m], self.ldm), dtype=torch.float64, device=dev)
@@ -69,14 +81,21 @@ class FusedExchange:
                     self.error = "symmetric memory works but the group has no multicast support"
                 self.bufs.append(b)
                 self.hdls.append(h)
+            self.flags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
+            self.flags_hdl = symm_mem.rendezvous(self.flags, self.group)
+            if not self.flags_hdl.multicast_ptr:
+                self.ok = False
+                self.error = "symmetric memory works but the group has no multicast support"
         except Exception as e:      # no symmetric memory in this environment
             self.ok = False
             self.error = f"{type(e).__name__}: {e}"
         self._barriers = 0                       # group barriers issued so far
+        self._epoch = 0                          # in-kernel barriers issued so far
         self._released_at = [-1] * tensor.nmodes  # barrier count when the buffer was last zeroed
         if self.ok:
             for b in self.bufs:
                 b.zero_()
+            self.flags.zero_()
             torch.cuda.synchronize()
             self._barrier(0)
             torch.cuda.synchronize()
@@ -101,9 +120,19 @@ class FusedExchange:
         if self._released_at[mode] == self._barriers:
             self._barrier(mode)      # no barrier since this buffer was zeroed: order it now
         s = torch.cuda.current_stream().cuda_stream
-        rc = lib.splatt_b200_mttkrp_multicast(
-            self.t.h, mode, self.R, self.ldm, ptrs,
-            C.cast(C.c_void_p(self.hdls[mode].multicast_ptr), A.val_p), C.c_void_p(s))
+        mc_out = C.cast(C.c_void_p(self.hdls[mode].multicast_ptr), A.val_p)
+        if self.kernel_barrier:
+            self._epoch += 1
+            gs = A.GroupSync(self.flags_hdl.multicast_ptr, self.flags.data_ptr(),
+                             (self._epoch * self.world) & 0xffffffff, 0)
+            rc = lib.splatt_b200_mttkrp_multicast_sync(self.t.h, mode, self.R, self.ldm, ptrs,
+                                                       mc_out, C.byref(gs), C.c_void_p(s))
+            if rc != A.SPLATT_SUCCESS:
+                raise RuntimeError(f"splatt_b200_mttkrp_multicast_sync failed ({rc})")
+            self._barriers += 1          # the kernel's tail IS a group barrier
+            return self.bufs[mode]
+        rc = lib.splatt_b200_mttkrp_multicast(self.t.h, mode, self.R, self.ldm, ptrs, mc_out,
+                                              C.c_void_p(s))
         if rc != A.SPLATT_SUCCESS:
             raise RuntimeError(f"splatt_b200_mttkrp_multicast failed ({rc})")
         self._barrier(mode)
@@ -120,8 +149,11 @@ def cpd_als_sharded(tensor, ncolumns, init_factors, ttnormsq, niters=50, tol=1e-
     """CPD-ALS over a sharded tensor: one process per GPU.
 
     Per mode: MTTKRP of this rank's shard, summed over ranks (fused NVLink-multicast exchange
-    when available and `fused`, else NCCL all-reduce), then the dense tail replicated on every
-    rank with the same device kernels `splatt_cpd_als` uses (`splatt_b200_als_tail_*`).  The
+    when available and `fused`, else NCCL all-reduce), then the dense tail ONCE, on rank 0,
+    with the same device kernels `splatt_cpd_als` uses (`splatt_b200_als_tail_*`); the new
+    factor is broadcast.  Factors are therefore single-valued: replicated tails agree only
+    to rounding (atomics and multimem.red arrive in a different order on every GPU) and on
+    ill-conditioned problems such replicas drift apart over the iterations.  The
     iteration is the reference's (src/cpd.c:318-373).  Also runs unsharded (no process group).
 
     init_factors: list of torch CUDA float64 (dims[m] x ncolumns) -- identical on every rank.
@@ -149,6 +181,9 @@ def cpd_als_sharded(tensor, ncolumns, init_factors, ttnormsq, niters=50, tol=1e-
     outs = [torch.empty((tensor.dims[m], ldm), dtype=torch.float64, device=dev) for m in range(N)]
     views = [a[:, :R] for a in mats]
     stream = torch.cuda.current_stream().cuda_stream
+    rank = dist.get_rank(group) if world > 1 else 0
+    src0 = (dist.get_global_rank(group, 0) if group is not None else 0) if world > 1 else 0
+    lead = rank == 0
     h = C.c_void_p()
     rc = lib.splatt_b200_als_tail_create(N, R, ldm, C.c_void_p(stream), C.byref(h))
     if rc != A.SPLATT_SUCCESS:
@@ -157,8 +192,9 @@ def cpd_als_sharded(tensor, ncolumns, init_factors, ttnormsq, niters=50, tol=1e-
     def ptr(t):
         return C.cast(C.c_void_p(t.data_ptr()), A.val_p)
     try:
-        for m in range(N):
-            lib.splatt_b200_als_tail_gram(h, m, ptr(mats[m]), tensor.dims[m])
+        if lead:
+            for m in range(N):
+                lib.splatt_b200_als_tail_gram(h, m, ptr(mats[m]), tensor.dims[m])
         fit = oldfit = 0.0
         lam = np.zeros(R)
         lam_c = (C.c_double * R)()
@@ -172,20 +208,37 @@ def cpd_als_sharded(tensor, ncolumns, init_factors, ttnormsq, niters=50, tol=1e-
                 else:
                     tensor.mttkrp(m, mats, outs[m], ncolumns=R)
                     m1 = all_reduce_output(outs[m], group)
-                rc = lib.splatt_b200_als_tail_update(h, m, ptr(m1), ptr(mats[m]), tensor.dims[m],
-                                                     1 if it == 0 else 0)
-                if rc != A.SPLATT_SUCCESS:
-                    raise RuntimeError("splatt_b200_als_tail_update failed")
+                if lead:
+                    rc = lib.splatt_b200_als_tail_update(h, m, ptr(m1), ptr(mats[m]),
+                                                         tensor.dims[m], 1 if it == 0 else 0)
+                    if rc != A.SPLATT_SUCCESS:
+                        raise RuntimeError("splatt_b200_als_tail_update failed")
+                if world > 1:
+                    dist.broadcast(mats[m], src=src0, group=group)    # one factor for everybody
                 last_m1 = m1
                 if fx is not None and m != N - 1:
                     fx.release(m)
             f = C.c_double()
-            rc = lib.splatt_b200_als_tail_fit(h, ptr(mats[N - 1]), ptr(last_m1), tensor.dims[N - 1],
-                                              float(ttnormsq), C.byref(f), lam_c)
+            if lead:
+                rc = lib.splatt_b200_als_tail_fit(h, ptr(mats[N - 1]), ptr(last_m1),
+                                                  tensor.dims[N - 1], float(ttnormsq), C.byref(f),
+                                                  lam_c)
+                if rc != A.SPLATT_SUCCESS:
+                    raise RuntimeError("splatt_b200_als_tail_fit failed")
             if fx is not None:
                 fx.release(N - 1)
             fit = f.value
             lam = np.array(lam_c[:])
+            if world > 1:
+                # one fit, one stop decision for the whole group (the reference all-reduces its
+                # fit, src/mpi/mpi_cpd.c:760-775)
+                ft = torch.zeros(1 + R, dtype=torch.float64, device=dev)
+                if lead:
+                    ft[0] = fit
+                    ft[1:] = torch.from_numpy(lam).to(dev)
+                dist.broadcast(ft, src=src0, group=group)
+                fh = ft.cpu().numpy()
+                fit, lam = float(fh[0]), fh[1:].copy()
             times.append(time.perf_counter() - t0)
             if verbose:
                 print(f"  its = {it + 1:3d} ({times[-1]:.4f}s)  fit = {fit:.5f}  "

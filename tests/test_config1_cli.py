@@ -52,19 +52,31 @@ GPU_CLI = ref.CLI_PATH.parent / "splatt_gpu"
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not GPU_CLI.exists(), reason="oracle/_ref/splatt_gpu not built")
+@pytest.mark.parametrize("gpus", ["one", "list-0,0", "ngpus-2"])
 @pytest.mark.parametrize("name,rank", [("med", 16), ("med4", 8), ("med5", 5)])
-def test_reference_cli_linked_against_libsplatt_b200(tmp_path, name, rank):
+def test_reference_cli_linked_against_libsplatt_b200(tmp_path, name, rank, gpus):
     """The drop-in, end to end: the UNMODIFIED reference CLI (tt_read, csf_alloc, cpd_als_iterate,
     LAPACK solve -- all reference code) with only its four MTTKRP symbols resolved from
     libsplatt_b200.so (objcopy rename, INTEGRATION.md option A).  Same seed => the GPU-backed run
-    prints the same fit trajectory as the pure-CPU run."""
+    prints the same fit trajectory as the pure-CPU run.  `gpus`: one GPU; the single-process
+    multi-GPU engine on a device list that names GPU 0 twice (SPLATT_B200_DEVICES=0,0); and
+    SPLATT_B200_NGPUS=2 on two real GPUs (gpurun --gpus 2) -- the reference's C host driving
+    several GPUs through the unchanged C API (the shape of src/mpi/mpi_cpd.c:627-804)."""
+    import torch
+    env = dict(os.environ)
+    if gpus == "list-0,0":
+        env["SPLATT_B200_DEVICES"] = "0,0"
+    elif gpus == "ngpus-2":
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+        env["SPLATT_B200_NGPUS"] = "2"
     z = np.load(GOLD / f"{name}.npz")
     tns = tmp_path / f"{name}.tns"
     _write_tns(tns, z["ind"], z["vals"])
     args = ["cpd", str(tns), "-r", str(rank), "-t", "2", "--seed", "3", "--nowrite", "-i", "6",
             "--tol", "0"]
     cpu = subprocess.run([str(ref.CLI_PATH)] + args, capture_output=True, text=True, timeout=300)
-    gpu = subprocess.run([str(GPU_CLI)] + args, capture_output=True, text=True, timeout=300)
+    gpu = subprocess.run([str(GPU_CLI)] + args, capture_output=True, text=True, timeout=300, env=env)
     assert cpu.returncode == 0 and gpu.returncode == 0, gpu.stderr
     f_cpu = re.findall(r"fit = ([0-9.]+)  delta = ([-+0-9.e]+)", cpu.stdout)
     f_gpu = re.findall(r"fit = ([0-9.]+)  delta = ([-+0-9.e]+)", gpu.stdout)

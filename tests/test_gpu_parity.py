@@ -316,6 +316,114 @@ def test_pinned_dropin_path(S, refmod, monkeypatch, R):
         ws.free()
 
 
+def test_pinned_shared_maxdim_output(S, refmod, monkeypatch):
+    """SPLATT_B200_PIN=1 with ONE output buffer of maxdim x R reused for every mode, smallest
+    mode first -- what the reference's CPD driver does (src/cpd.c:322-327): the registration
+    must grow with the extent actually used."""
+    monkeypatch.setenv("SPLATT_B200_PIN", "1")
+    dims, inds, vals = random_coo((40, 900, 300), 30000, seed=5)
+    R = 16
+    mats = factor_mats(dims, R)
+    tt, gold = _gold(refmod, dims, inds, vals, mats)
+    o = refmod.default_opts()
+    csf = refmod.RefCsf(tt, o)
+    ws = S.MttkrpWorkspace(csf.ptr, R, o)
+    shared = np.empty((max(dims), R))
+    for _ in range(2):
+        for m in range(3):
+            out = shared[:dims[m]]
+            ws.mttkrp_csf(mats, m, out)
+            assert rel_fro(out, gold[m]) < TOL, m
+    ws.free()
+
+
+@pytest.mark.parametrize("stage", ["0", "1"])
+@pytest.mark.parametrize("R", [5, 32])
+def test_pageable_paths(S, refmod, monkeypatch, stage, R):
+    """Pageable caller buffers: staged through the workspace's page-locked bounce buffers
+    (default) or handed to cudaMemcpy directly (SPLATT_B200_STAGE=0)."""
+    monkeypatch.setenv("SPLATT_B200_STAGE", stage)
+    dims, inds, vals = _tensor("t3_skew")
+    mats = factor_mats(dims, R)
+    tt, gold = _gold(refmod, dims, inds, vals, mats)
+    o = refmod.default_opts()
+    csf = refmod.RefCsf(tt, o)
+    ws = S.MttkrpWorkspace(csf.ptr, R, o)
+    for _ in range(2):
+        for m in range(3):
+            out = np.full((dims[m], R), np.nan)
+            ws.mttkrp_csf(mats, m, out)
+            assert rel_fro(out, gold[m]) < TOL, (stage, R, m)
+    ws.free()
+
+
+def test_bare_mttkrp_reuses_device_mirror(S, refmod, monkeypatch):
+    """splatt_mttkrp (no workspace handle; matlab/splatt_mttkrp.c:68) builds the device
+    mirror once per tensor: later calls find it in the cache (no stream build), a different
+    tensor gets its own, and a tensor whose content changed in place is rebuilt."""
+    monkeypatch.setenv("SPLATT_B200_CACHE", "2")
+    S.cache_clear()
+    dims, inds, vals = _tensor("t3_mid")
+    R = 8
+    mats = factor_mats(dims, R)
+    tt, gold = _gold(refmod, dims, inds, vals, mats)
+    o = refmod.default_opts()
+    csf = refmod.RefCsf(tt, o)
+    b0 = S.build_count()
+    for rep in range(3):
+        for m in range(3):
+            assert rel_fro(S.mttkrp(m, R, csf.ptr, mats, o), gold[m]) < TOL
+        if rep == 0:
+            b1 = S.build_count()
+            assert b1 - b0 == 3            # one stream per mode (ALLROOT), built on the first call
+    assert S.build_count() == b1           # 8 more calls, no rebuild
+    # another tensor: its own mirror; the first one is still cached
+    d2, i2, v2 = _tensor("t4")
+    m2 = factor_mats(d2, R)
+    tt2, gold2 = _gold(refmod, d2, i2, v2, m2)
+    csf2 = refmod.RefCsf(tt2, o)
+    assert rel_fro(S.mttkrp(0, R, csf2.ptr, m2, o), gold2[0]) < TOL
+    b2 = S.build_count()
+    assert b2 - b1 == 4
+    assert rel_fro(S.mttkrp(1, R, csf.ptr, mats, o), gold[1]) < TOL
+    assert S.build_count() == b2
+    # values changed in place (same addresses): the fingerprint must not match
+    arr = csf.ptr[0].pt[0].vals
+    n = int(csf.ptr[0].nnz)
+    for c in range(csf.count):
+        v = csf.ptr[c].pt[0].vals
+        for i in range(n):
+            v[i] = 2.0 * v[i]
+    assert rel_fro(S.mttkrp(2, R, csf.ptr, mats, o), 2.0 * gold[2]) < TOL
+    assert S.build_count() > b2
+    del arr
+    S.cache_clear()
+    # cache off: rebuilt on every call, same answers
+    monkeypatch.setenv("SPLATT_B200_CACHE", "0")
+    b3 = S.build_count()
+    assert rel_fro(S.mttkrp(0, R, csf2.ptr, m2, o), gold2[0]) < TOL
+    assert rel_fro(S.mttkrp(0, R, csf2.ptr, m2, o), gold2[0]) < TOL
+    assert S.build_count() - b3 == 8
+
+
+def test_cpd_als_rank_128_device_tail(S, refmod):
+    """Rank 128: the device tail's shared-memory needs (R*R + R*rows doubles for the row
+    solve, R*R for the Cholesky) must be sized to the device, not assumed (round-1 advice):
+    results still track the compiled reference."""
+    dims, inds, vals = random_coo((300, 250, 200), 60000, seed=13)
+    dims, inds, vals = cover_all_slices(dims, inds, vals)
+    R = 128
+    o = refmod.default_opts()
+    o[0], o[3], o[1], o[4] = 4, 3, 0.0, 0
+    tt = refmod.RefTensor.from_coo(dims, inds, vals)
+    csf = refmod.RefCsf(tt, o)
+    fit_ref, lam_ref, fac_ref = csf.cpd_als(R, seed=5)
+    fit, lam, fac = S.cpd_als(csf.ptr, R, o, seed=5)
+    assert np.isfinite(fit)
+    assert abs(fit - fit_ref) < 1e-7, (fit, fit_ref)
+    assert np.allclose(lam, lam_ref, rtol=1e-5, atol=1e-8)
+
+
 def test_alias_output_with_own_factor(S, refmod):
     """matrices[mode] may alias matout (matlab/splatt_mttkrp.c:47-68)."""
     dims, inds, vals = _tensor("t3_mid")

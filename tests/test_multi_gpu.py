@@ -205,3 +205,51 @@ def test_splatt_cpd_als_honours_device_list(S, refmod, monkeypatch):
     fit, lam, fac = S.cpd_als(csf.ptr, 6, o, seed=11)
     assert abs(fit - fit_ref) < 1e-8
     csf.free()
+
+
+def test_multi_cpd_factors_stay_single_valued(S, refmod):
+    """An ill-conditioned problem (rank 32 on a 300^3 random tensor): with a tail replicated
+    on every device the factor replicas drift apart within ~10 iterations and the fit blows up
+    (measured on 2 GPUs).  The engine runs the tail once and hands the factor to the other
+    devices, so many iterations later it still tracks the single-GPU run."""
+    dims, inds, vals = random_coo((300, 300, 300), 200000, seed=21)
+    dims, inds, vals = cover_all_slices(dims, inds, vals)
+    R = 32
+    o = refmod.default_opts()
+    o[0], o[3], o[1], o[4] = 1, 16, 0.0, 0
+    tt = refmod.RefTensor.from_coo(dims, inds, vals)
+    csf = refmod.RefCsf(tt, o)
+    fit1, _, _ = S.cpd_als(csf.ptr, R, o, seed=3)
+    assert 0.0 < fit1 < 1.0
+    for devs in _devlists():
+        mg = S.MultiGpu(csf.ptr, int(o[6]), R, devs)
+        fit, lam, fac = mg.cpd_als(o, seed=3)
+        assert np.isfinite(fit) and abs(fit - fit1) < 1e-5, (devs, fit, fit1)
+        mg.free()
+    csf.free()
+
+
+def test_real_gpus_use_the_multicast_exchange(S, refmod):
+    """On an NVSwitch box the engine must come up with the fused multicast exchange (the
+    peer-reduce path is only the fallback); SPLATT_B200_MULTICAST=0 forces the fallback."""
+    import os
+    if _ngpus() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    dims, inds, vals = _tensor("t3_mid")
+    tt = refmod.RefTensor.from_coo(dims, inds, vals)
+    o = refmod.default_opts()
+    csf = refmod.RefCsf(tt, o)
+    mg = S.MultiGpu(csf.ptr, int(o[6]), 8, [0, 1])
+    assert mg.multicast or os.environ.get("SPLATT_B200_MULTICAST") == "0"
+    mg.free()
+    os.environ["SPLATT_B200_MULTICAST"] = "0"
+    try:
+        mg = S.MultiGpu(csf.ptr, int(o[6]), 8, [0, 1])
+        assert not mg.multicast
+        mats = factor_mats(dims, 8)
+        gold = tt.mttkrp_stream(mats, 1)
+        assert rel_fro(mg.mttkrp_host(1, mats), gold) < TOL
+        mg.free()
+    finally:
+        os.environ.pop("SPLATT_B200_MULTICAST")
+    csf.free()

@@ -379,11 +379,13 @@ __global__ void k_form_chol(const double * __restrict__ ata, int nmodes, int mod
 // laid out [r][thread] so that accesses are conflict-free; L is read as a broadcast.
 __global__ void k_solve_rows(const double * __restrict__ M1, double * __restrict__ X,
                              unsigned long long I, int R, int ld, const double * __restrict__ L,
-                             const double * __restrict__ P, const int * __restrict__ info) {
+                             const double * __restrict__ P, const int * __restrict__ info,
+                             int only_fallback) {
   extern __shared__ double sm[];
   double * Ls = sm;                         // R*R
   double * xs = sm + R * R;                 // R * blockDim.x
   const bool use_p = (*info != 0);
+  if (only_fallback && !use_p) return;      // the register-tiled kernel did the work
   const double * src = use_p ? P : L;
   for (int x = threadIdx.x; x < R * R; x += blockDim.x) Ls[x] = src[x];
   __syncthreads();
@@ -412,6 +414,146 @@ __global__ void k_solve_rows(const double * __restrict__ M1, double * __restrict
       for (int k = 0; k < R; ++k) s = fma(xs[k * T + t], Ls[j + k * R], s);
       out[j] = s;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Register-tiled versions of the two O(I R^2) steps for R <= 64 (RT = R padded to 16/32/64).
+// The generic kernels above spend two shared-memory reads per fp64 FMA (ncu launch list of
+// one ALS iteration, profiles/r02_cpd_tail.md: 1M x 64 factor: k_solve_rows 2.76 ms, k_gram
+// 1.2 ms -- 41 % of the iteration); here the row / the 4x4 output block lives in registers.
+// ---------------------------------------------------------------------------
+
+// X[i,:] = M1[i,:] * (L L^T)^-1, one thread per row, the row in registers, L (padded with an
+// identity block to RT) and its transpose in shared memory, read as 128-bit broadcasts.
+// reference: potrs call src/matrix.c:563.  (*info != 0: the generic kernel handles it.)
+template <int RT>
+__global__ void __launch_bounds__(128)
+k_solve_rows_reg(const double * __restrict__ M1, double * __restrict__ X, unsigned long long I,
+                 int R, int ld, const double * __restrict__ L, const int * __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double * Ls  = sm;                    // RT*RT, row-major lower factor
+  double * Lt  = sm + RT * RT;          // its transpose
+  double * inv = sm + 2 * RT * RT;      // 1 / diagonal
+  if (*info != 0) return;
+  for (int x = threadIdx.x; x < RT * RT; x += blockDim.x) {
+    const int i = x / RT, j = x % RT;
+    double v;
+    if (i < R && j < R) v = (j <= i) ? L[j + i * R] : 0.0;
+    else v = (i == j) ? 1.0 : 0.0;
+    Ls[i * RT + j] = v;
+    Lt[j * RT + i] = v;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < RT; x += blockDim.x) inv[x] = 1.0 / Ls[x * RT + x];
+  __syncthreads();
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  double x[RT];
+  const double * row = M1 + i * ld;
+#pragma unroll
+  for (int r = 0; r < RT; r += 2) {
+    if (r + 1 < R) { const double2 v = *reinterpret_cast<const double2 *>(row + r); x[r] = v.x; x[r + 1] = v.y; }
+    else { x[r] = (r < R) ? row[r] : 0.0; x[r + 1] = 0.0; }
+  }
+  // L y = x (forward), four independent partial sums per entry
+#pragma unroll
+  for (int p = 0; p < RT; ++p) {
+    double s0 = x[p], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < p; k += 2) {
+      const double2 l = *reinterpret_cast<const double2 *>(&Ls[p * RT + k]);
+      if ((k & 2) == 0) { s0 = fma(-l.x, x[k], s0); s1 = fma(-l.y, x[k + 1], s1); }
+      else              { s2 = fma(-l.x, x[k], s2); s3 = fma(-l.y, x[k + 1], s3); }
+    }
+    if (p & 1) s0 = fma(-Ls[p * RT + p - 1], x[p - 1], s0);
+    x[p] = ((s0 + s1) + (s2 + s3)) * inv[p];
+  }
+  // L^T z = y (backward)
+#pragma unroll
+  for (int p = RT - 1; p >= 0; --p) {
+    double s0 = x[p], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    constexpr int dummy = 0; (void)dummy;
+    const int k0 = p + 1 + ((p + 1) & 1);          // first even index above p
+    if ((p + 1) & 1) { if (p + 1 < RT) s0 = fma(-Lt[p * RT + p + 1], x[p + 1], s0); }
+#pragma unroll
+    for (int k = 0; k < RT; k += 2) {
+      if (k >= k0) {
+        const double2 l = *reinterpret_cast<const double2 *>(&Lt[p * RT + k]);
+        if ((k & 2) == 0) { s0 = fma(-l.x, x[k], s0); s1 = fma(-l.y, x[k + 1], s1); }
+        else              { s2 = fma(-l.x, x[k], s2); s3 = fma(-l.y, x[k + 1], s3); }
+      }
+    }
+    x[p] = ((s0 + s1) + (s2 + s3)) * inv[p];
+  }
+  double * out = X + i * ld;
+#pragma unroll
+  for (int r = 0; r < RT; r += 2) {
+    if (r + 1 < R) *reinterpret_cast<double2 *>(out + r) = make_double2(x[r], x[r + 1]);
+    else if (r < R) out[r] = x[r];
+  }
+}
+
+// G(upper, row-major R x R) += A^T A as a register-tiled SYRK: persistent CTAs stream
+// 64-row tiles of A through shared memory; two teams of threads (even / odd tile rows) each
+// hold the 4x4 blocks of the upper triangle of G in registers (one block per thread) and
+// flush them with one round of atomics per CTA.  reference: mat_aTa src/matrix.c:414-455
+template <int RT>
+__global__ void __launch_bounds__(2 * ((RT / 4) * (RT / 4 + 1) / 2 + 31) / 32 * 32)
+k_gram_syrk(const double * __restrict__ A, unsigned long long I, int R, int lda,
+            double * __restrict__ G) {
+  constexpr int NB     = RT / 4;                       // 4x4 blocks per side
+  constexpr int NBLK   = NB * (NB + 1) / 2;            // blocks of the upper triangle
+  constexpr int TEAM   = (NBLK + 31) / 32 * 32;        // threads per team (whole warps)
+  constexpr int TR     = 64;                           // rows per tile
+  extern __shared__ __align__(16) double tile[];       // TR x RT
+  const int team = threadIdx.x / TEAM, t = threadIdx.x % TEAM;
+  // block t -> (bp, bq >= bp)
+  int bp = 0, rem = t;
+  while (bp < NB && rem >= NB - bp) { rem -= NB - bp; ++bp; }
+  const bool active = t < NBLK;
+  const int p0 = 4 * bp, q0 = 4 * (bp + rem);
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  // zero the padding columns once
+  for (int x = threadIdx.x; x < TR * RT; x += blockDim.x) tile[x] = 0.0;
+  __syncthreads();
+  for (unsigned long long r0 = (unsigned long long)blockIdx.x * TR; r0 < I;
+       r0 += (unsigned long long)gridDim.x * TR) {
+    const int rows = (int)min((unsigned long long)TR, I - r0);
+    for (int x = threadIdx.x; x < TR * R; x += blockDim.x) {
+      const int i = x / R, j = x % R;
+      tile[i * RT + j] = (i < rows) ? A[(r0 + i) * lda + j] : 0.0;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int i = team; i < TR; i += 2) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(&tile[i * RT + p0]);
+        const double2 a23 = *reinterpret_cast<const double2 *>(&tile[i * RT + p0 + 2]);
+        const double2 b01 = *reinterpret_cast<const double2 *>(&tile[i * RT + q0]);
+        const double2 b23 = *reinterpret_cast<const double2 *>(&tile[i * RT + q0 + 2]);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int p = p0 + a, q = q0 + b;
+        if (p < R && q < R && q >= p) atomicAdd(&G[q + p * R], acc[a][b]);
+      }
   }
 }
 
@@ -485,6 +627,7 @@ struct DevTail {
   double * h_back = nullptr;  // pinned: N*R*R + R + 1 (+1 info)
   cudaStream_t s = nullptr;
   int      solve_threads = 128;   // rows per block of k_solve_rows (shared memory permitting)
+  int      rt = 0;                // R padded to 16 / 32 / 64: register-tiled solve + SYRK (0 = generic)
   bool     failed = false;        // a launch was rejected: results are not to be trusted
 
   bool alloc(int N_, int R_, int ld_, cudaStream_t st) {
@@ -512,6 +655,19 @@ struct DevTail {
                                 (R * R + R * solve_threads) * 8) == cudaSuccess &&
            cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * R * 8) == cudaSuccess;
       if (!ok) fprintf(stderr, "SPLATT: rank %d does not fit the device ALS tail (shared memory)\n", R);
+      const char * ge = getenv("SPLATT_B200_TAIL_GENERIC");
+      rt = (ge && atoi(ge) != 0) ? 0 : (R <= 16 ? 16 : (R <= 32 ? 32 : (R <= 64 ? 64 : 0)));
+      if (ok && rt) {
+        const int sb = (2 * rt * rt + rt) * 8, gb = 64 * rt * 8;
+        cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+        if (rt == 16) { e1 = cudaFuncSetAttribute(k_solve_rows_reg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+                        e2 = cudaFuncSetAttribute(k_gram_syrk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gb); }
+        if (rt == 32) { e1 = cudaFuncSetAttribute(k_solve_rows_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+                        e2 = cudaFuncSetAttribute(k_gram_syrk<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gb); }
+        if (rt == 64) { e1 = cudaFuncSetAttribute(k_solve_rows_reg<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+                        e2 = cudaFuncSetAttribute(k_gram_syrk<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gb); }
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); rt = 0; }
+      }
     }
     return ok;
   }
@@ -530,8 +686,16 @@ struct DevTail {
   void gram(const double * A, uint64_t I, int m) {
     double * G = ata + (size_t)m * R * R;
     cudaMemsetAsync(G, 0, sizeof(double) * R * R, s);
-    const unsigned blocks = (unsigned)std::min<uint64_t>((I + 31) / 32, 592);
-    k_gram<<<blocks, 256, 32 * R * 8, s>>>(A, I, R, ld, G);
+    if (rt) {
+      const unsigned blocks = (unsigned)std::min<uint64_t>((I + 63) / 64, 296);
+      const size_t sm = (size_t)64 * rt * 8;
+      if (rt == 16) k_gram_syrk<16><<<blocks, 64, sm, s>>>(A, I, R, ld, G);
+      else if (rt == 32) k_gram_syrk<32><<<blocks, 128, sm, s>>>(A, I, R, ld, G);
+      else k_gram_syrk<64><<<blocks, 320, sm, s>>>(A, I, R, ld, G);
+    } else {
+      const unsigned blocks = (unsigned)std::min<uint64_t>((I + 31) / 32, 592);
+      k_gram<<<blocks, 256, 32 * R * 8, s>>>(A, I, R, ld, G);
+    }
     check("k_gram");
     spb200_count_launches(1);
   }
@@ -540,8 +704,21 @@ struct DevTail {
     k_form_chol<<<1, 256, R * R * 8, s>>>(ata, N, m, R, chol, pinv, jac_v, info);
     check("k_form_chol");
     const int T = solve_threads;
-    k_solve_rows<<<(unsigned)((I + T - 1) / T), T, (R * R + R * T) * 8, s>>>(
-        d_out, d_mat, I, R, ld, chol, pinv, info);
+    if (rt) {
+      // register-tiled solve when the Cholesky succeeded (it returns at once otherwise) ...
+      const size_t sm = (size_t)(2 * rt * rt + rt) * 8;
+      const unsigned nb = (unsigned)((I + 127) / 128);
+      if (rt == 16) k_solve_rows_reg<16><<<nb, 128, sm, s>>>(d_out, d_mat, I, R, ld, chol, info);
+      else if (rt == 32) k_solve_rows_reg<32><<<nb, 128, sm, s>>>(d_out, d_mat, I, R, ld, chol, info);
+      else k_solve_rows_reg<64><<<nb, 128, sm, s>>>(d_out, d_mat, I, R, ld, chol, info);
+      // ... and the generic kernel only for the pseudo-inverse fallback (info != 0)
+      k_solve_rows<<<(unsigned)((I + T - 1) / T), T, (R * R + R * T) * 8, s>>>(
+          d_out, d_mat, I, R, ld, chol, pinv, info, 1);
+      spb200_count_launches(1);
+    } else {
+      k_solve_rows<<<(unsigned)((I + T - 1) / T), T, (R * R + R * T) * 8, s>>>(
+          d_out, d_mat, I, R, ld, chol, pinv, info, 0);
+    }
     check("k_solve_rows");
     cudaMemsetAsync(lam_acc, 0, sizeof(double) * R, s);
     dim3 g((unsigned)std::min<uint64_t>((I + 7) / 8, 1184), (R + 31) / 32);

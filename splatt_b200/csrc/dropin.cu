@@ -131,7 +131,7 @@ int stage_threads() {
   static int v = 0;
   if (v == 0) {
     const char * e = getenv("SPLATT_B200_STAGE_THREADS");
-    v = e ? atoi(e) : 8;
+    v = e ? atoi(e) : 16;
     if (v < 1) v = 1;
     if (v > 64) v = 64;
   }

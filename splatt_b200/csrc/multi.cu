@@ -411,9 +411,9 @@ bool host_pinned(const void * p, size_t bytes) {
 }
 
 void par_memcpy(void * dst, const void * src, size_t bytes) {
-  const size_t chunk = 1 << 18;
+  const size_t chunk = 1 << 17;
   const int64_t n = (int64_t)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) num_threads(8)
+#pragma omp parallel for schedule(static) num_threads(16)
   for (int64_t c = 0; c < n; ++c) {
     const size_t o = (size_t)c * chunk;
     memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, std::min(chunk, bytes - o));

@@ -72,11 +72,13 @@ def build(verbose: bool = False) -> Path:
     newest = max(Path(o).stat().st_mtime for o in objs)
     if OUT.exists() and OUT.stat().st_mtime >= newest:
         return OUT
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *objs,
+    tmp = OUT.with_suffix(".so.tmp")      # link beside, then rename: never a half-written library
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(tmp), *objs,
            "-Xcompiler", "-fopenmp", "-Xlinker", "-Bsymbolic", "-lgomp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -181,3 +181,18 @@ int spb200_launch_tiled_root3(const FiberStream & s, int ncolumns, int ldm, uint
                               const double * leaf, const double * parent, double * d_out,
                               cudaStream_t stream);
 uint32_t spb200_tiled_rows_for(int ncolumns);   // rows of a leaf tile that fit the kernel's smem
+
+// cpd.cu -- row-partitioned ALS tail steps (multi-GPU engine).  Every device works on its own
+// row slice; partial column norms / Grams go to per-device slots of the multicast region and
+// are combined in device order on every device, so all replicas stay bit-identical.
+struct splatt_b200_als_tail;
+int spb200_tail_solve_norm_partial(splatt_b200_als_tail * h, int mode, const double * d_m1,
+                                   double * d_x, uint64_t rows, int first_iteration,
+                                   double * mc_norm_slot);
+int spb200_tail_scale_gram_partial(splatt_b200_als_tail * h, double * d_x, double * mc_x,
+                                   uint64_t rows, int first_iteration, const double * norms_all,
+                                   int k, int norm_stride, double * mc_gram_slot);
+int spb200_tail_gram_partial(splatt_b200_als_tail * h, const double * d_rows, uint64_t rows,
+                             double * mc_gram_slot);
+int spb200_tail_finish_gram(splatt_b200_als_tail * h, int mode, const double * grams_all, int k,
+                            int gram_stride);

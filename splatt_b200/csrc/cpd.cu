@@ -614,6 +614,48 @@ __global__ void k_inner(const double * __restrict__ A, const double * __restrict
   }
 }
 
+// ---- pieces of the ROW-PARTITIONED tail (multi-GPU engine, multi.cu): every device works on
+// its own row slice and publishes partial column norms / partial Grams into per-device slots
+// of the group's multicast region; all devices then combine the slots in device order, so
+// they all end up with bit-identical lambda, Grams and factors.
+
+// publish n doubles to a (multicast) address; zero the source for its next accumulation
+__global__ void k_publish_zero(double * __restrict__ src, double * __restrict__ dst, int n) {
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+    dst[x] = src[x];
+    src[x] = 0.0;
+  }
+}
+// lambda from k per-device partial vectors (sum of squares -> sqrt, or max -> max(., 1))
+__global__ void k_lambda_from_partials(const double * __restrict__ parts, int k, int stride, int R,
+                                       int two_norm, double * __restrict__ lambda) {
+  const int j = threadIdx.x + blockIdx.x * blockDim.x;
+  if (j >= R) return;
+  double v = 0.0;
+  for (int d = 0; d < k; ++d) v = two_norm ? v + parts[(size_t)d * stride + j] : fmax(v, parts[(size_t)d * stride + j]);
+  lambda[j] = two_norm ? sqrt(v) : fmax(v, 1.0);
+}
+// rows /= lambda, written to the local replica and (multicast) to every replica
+__global__ void k_scale_rows_mc(double * __restrict__ x_local, double * __restrict__ x_mc,
+                                unsigned long long I, int R, int ld, const double * __restrict__ lambda) {
+  const unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= I * R) return;
+  const unsigned long long i = x / R;
+  const int j = (int)(x % R);
+  const double v = x_local[i * ld + j] / lambda[j];
+  x_local[i * ld + j] = v;
+  x_mc[i * ld + j] = v;
+}
+// dst = sum over devices of the published partials, in device order
+__global__ void k_sum_partials(const double * __restrict__ parts, int k, int stride, int n,
+                               double * __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  double v = 0.0;
+  for (int d = 0; d < k; ++d) v += parts[(size_t)d * stride + x];
+  dst[x] = v;
+}
+
 struct DevTail {
   int N = 0, R = 0, ld = 0;
   double * ata = nullptr;     // N x R x R
@@ -624,6 +666,7 @@ struct DevTail {
   double * inner = nullptr;   // 1
   int *    info = nullptr;
   double * jac_v = nullptr;   // R x R scratch of the pseudo-inverse fallback
+  double * gpart = nullptr;   // R x R partial Gram of a row slice (zero between uses)
   double * h_back = nullptr;  // pinned: N*R*R + R + 1 (+1 info)
   cudaStream_t s = nullptr;
   int      solve_threads = 128;   // rows per block of k_solve_rows (shared memory permitting)
@@ -640,6 +683,9 @@ struct DevTail {
               cudaMalloc(&inner, sizeof(double)) == cudaSuccess &&
               cudaMalloc(&info, sizeof(int) * 2) == cudaSuccess &&
               cudaMalloc(&jac_v, sizeof(double) * R * R) == cudaSuccess &&
+              cudaMalloc(&gpart, sizeof(double) * R * R) == cudaSuccess &&
+              cudaMemset(gpart, 0, sizeof(double) * R * R) == cudaSuccess &&
+              cudaMemset(lam_acc, 0, sizeof(double) * R) == cudaSuccess &&
               cudaMallocHost(&h_back, sizeof(double) * ((size_t)N * R * R + R + 2)) == cudaSuccess;
     if (ok) {
       // shared-memory budgets: k_form_chol R*R doubles (128 KB at R = 128); k_solve_rows
@@ -680,12 +726,17 @@ struct DevTail {
   }
   void release() {
     cudaFree(ata); cudaFree(chol); cudaFree(pinv); cudaFree(lam_acc); cudaFree(lambda);
-    cudaFree(inner); cudaFree(info); cudaFree(jac_v);
+    cudaFree(inner); cudaFree(info); cudaFree(jac_v); cudaFree(gpart);
     if (h_back) cudaFreeHost(h_back);
   }
   void gram(const double * A, uint64_t I, int m) {
     double * G = ata + (size_t)m * R * R;
     cudaMemsetAsync(G, 0, sizeof(double) * R * R, s);
+    gram_into(A, I, G);
+  }
+  // G += A^T A (G is NOT zeroed here)
+  void gram_into(const double * A, uint64_t I, double * G) {
+    if (I == 0) return;
     if (rt) {
       const unsigned blocks = (unsigned)std::min<uint64_t>((I + 63) / 64, 296);
       const size_t sm = (size_t)64 * rt * 8;
@@ -701,8 +752,22 @@ struct DevTail {
   }
   // one mode step after the MTTKRP: d_out (M1) -> d_mat (new factor), lambda, Gram
   void mode_step(const double * d_out, double * d_mat, uint64_t I, int m, bool two_norm) {
+    solve(d_out, d_mat, I, m);
+    cudaMemsetAsync(lam_acc, 0, sizeof(double) * R, s);
+    dim3 g((unsigned)std::min<uint64_t>((I + 7) / 8, 1184), (R + 31) / 32);
+    k_colnorm<<<g, 256, 0, s>>>(d_mat, I, R, ld, two_norm ? 1 : 0, lam_acc);
+    k_finish_lambda<<<(R + 127) / 128, 128, 0, s>>>(lam_acc, R, two_norm ? 1 : 0, lambda);
+    k_scale_cols<<<(unsigned)((I * R + 255) / 256), 256, 0, s>>>(d_mat, I, R, ld, lambda);
+    check("normalise");
+    spb200_count_launches(3);
+    gram(d_mat, I, m);
+  }
+  // normal matrix of mode m + Cholesky, then the row solves of `I` rows
+  void solve(const double * d_out, double * d_mat, uint64_t I, int m) {
     k_form_chol<<<1, 256, R * R * 8, s>>>(ata, N, m, R, chol, pinv, jac_v, info);
     check("k_form_chol");
+    spb200_count_launches(1);
+    if (I == 0) return;
     const int T = solve_threads;
     if (rt) {
       // register-tiled solve when the Cholesky succeeded (it returns at once otherwise) ...
@@ -720,14 +785,42 @@ struct DevTail {
           d_out, d_mat, I, R, ld, chol, pinv, info, 0);
     }
     check("k_solve_rows");
-    cudaMemsetAsync(lam_acc, 0, sizeof(double) * R, s);
-    dim3 g((unsigned)std::min<uint64_t>((I + 7) / 8, 1184), (R + 31) / 32);
-    k_colnorm<<<g, 256, 0, s>>>(d_mat, I, R, ld, two_norm ? 1 : 0, lam_acc);
-    k_finish_lambda<<<(R + 127) / 128, 128, 0, s>>>(lam_acc, R, two_norm ? 1 : 0, lambda);
-    k_scale_cols<<<(unsigned)((I * R + 255) / 256), 256, 0, s>>>(d_mat, I, R, ld, lambda);
-    check("normalise");
-    spb200_count_launches(5);
-    gram(d_mat, I, m);
+    spb200_count_launches(1);
+  }
+
+  // ---- row-partitioned tail (see the kernels above)
+  void solve_norm_partial(const double * m1, double * x, uint64_t rows, int m, bool two_norm,
+                          double * mc_norm_slot) {
+    solve(m1, x, rows, m);
+    if (rows) {
+      dim3 g((unsigned)std::min<uint64_t>((rows + 7) / 8, 1184), (R + 31) / 32);
+      k_colnorm<<<g, 256, 0, s>>>(x, rows, R, ld, two_norm ? 1 : 0, lam_acc);
+    }
+    k_publish_zero<<<1, 128, 0, s>>>(lam_acc, mc_norm_slot, R);
+    check("norm partial");
+    spb200_count_launches(2);
+  }
+  void scale_gram_partial(double * x, double * x_mc, uint64_t rows, bool two_norm,
+                          const double * norms_all, int k, int norm_stride, double * mc_gram_slot) {
+    k_lambda_from_partials<<<(R + 127) / 128, 128, 0, s>>>(norms_all, k, norm_stride, R,
+                                                           two_norm ? 1 : 0, lambda);
+    if (rows)
+      k_scale_rows_mc<<<(unsigned)((rows * R + 255) / 256), 256, 0, s>>>(x, x_mc, rows, R, ld, lambda);
+    gram_partial(x, rows, mc_gram_slot);
+    check("scale + gram partial");
+    spb200_count_launches(2);
+  }
+  void gram_partial(const double * x, uint64_t rows, double * mc_gram_slot) {
+    gram_into(x, rows, gpart);
+    k_publish_zero<<<(R * R + 255) / 256, 256, 0, s>>>(gpart, mc_gram_slot, R * R);
+    check("gram partial");
+    spb200_count_launches(1);
+  }
+  void finish_gram(int m, const double * grams_all, int k, int gram_stride) {
+    k_sum_partials<<<(R * R + 255) / 256, 256, 0, s>>>(grams_all, k, gram_stride, R * R,
+                                                        ata + (size_t)m * R * R);
+    check("gram sum");
+    spb200_count_launches(1);
   }
 };
 
@@ -996,6 +1089,35 @@ int splatt_b200_als_tail_fit(splatt_b200_als_tail * h, double const * d_last_fac
   if (lambda_out) memcpy(lambda_out, lambda, sizeof(double) * R);
   return SPLATT_SUCCESS;
 }
+
+}  // extern "C"
+
+// Row-partitioned tail steps for the multi-GPU engine (internal, see common.h).
+int spb200_tail_solve_norm_partial(splatt_b200_als_tail * h, int mode, const double * d_m1,
+                                   double * d_x, uint64_t rows, int first_iteration,
+                                   double * mc_norm_slot) {
+  h->t.solve_norm_partial(d_m1, d_x, rows, mode, first_iteration != 0, mc_norm_slot);
+  return h->t.failed ? SPLATT_ERROR_BADINPUT : SPLATT_SUCCESS;
+}
+int spb200_tail_scale_gram_partial(splatt_b200_als_tail * h, double * d_x, double * mc_x,
+                                   uint64_t rows, int first_iteration, const double * norms_all,
+                                   int k, int norm_stride, double * mc_gram_slot) {
+  h->t.scale_gram_partial(d_x, mc_x, rows, first_iteration != 0, norms_all, k, norm_stride,
+                          mc_gram_slot);
+  return h->t.failed ? SPLATT_ERROR_BADINPUT : SPLATT_SUCCESS;
+}
+int spb200_tail_gram_partial(splatt_b200_als_tail * h, const double * d_rows, uint64_t rows,
+                             double * mc_gram_slot) {
+  h->t.gram_partial(d_rows, rows, mc_gram_slot);
+  return h->t.failed ? SPLATT_ERROR_BADINPUT : SPLATT_SUCCESS;
+}
+int spb200_tail_finish_gram(splatt_b200_als_tail * h, int mode, const double * grams_all, int k,
+                            int gram_stride) {
+  h->t.finish_gram(mode, grams_all, k, gram_stride);
+  return h->t.failed ? SPLATT_ERROR_BADINPUT : SPLATT_SUCCESS;
+}
+
+extern "C" {
 
 void splatt_free_kruskal(splatt_kruskal * factored) {
   if (!factored) return;

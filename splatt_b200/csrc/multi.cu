@@ -218,6 +218,20 @@ __global__ void k_peer_reduce(const PeerReduceArgs a, unsigned long long e0, uns
   }
 }
 
+// Stand-alone group barrier (same flag and arrival count as the MTTKRP kernel's tail): the
+// kernels before it on this stream have completed, so their multicast stores are performed;
+// signal every GPU, wait until every GPU has signalled.
+__global__ void k_group_barrier(uint32_t * mc_flag, uint32_t * local_flag, uint32_t target) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flag), "r"(1u) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flag) : "memory");
+    } while (static_cast<int>(v - target) < 0);
+  }
+}
+
 struct DevState {
   int dev = 0;
   splatt_b200_tensor * T = nullptr;
@@ -226,6 +240,8 @@ struct DevState {
   double * out[SPB200_MAXN] = {nullptr};    // this device's (unicast) output buffer per mode
   double * part = nullptr;                  // fallback: local partial, maxdim x ldm
   uint32_t * flag_local = nullptr;
+  double * norms_local = nullptr;           // this device's copy of the k norm slots
+  double * grams_local = nullptr;           // ... and of the k Gram slots
   cudaEvent_t ev_k = nullptr, ev_r = nullptr;
   cudaEvent_t ev_tail = nullptr;            // device 0: the mode's new factor is ready
   splatt_b200_als_tail * tail = nullptr;    // device 0 only (see splatt_b200_multi_cpd_als)
@@ -254,7 +270,13 @@ struct splatt_b200_multi {
   bool distinct = true;            // all devices distinct (false only in tests: "0,0")
   McRegion mc;
   size_t out_off[SPB200_MAXN] = {0};
+  size_t mat_off[SPB200_MAXN] = {0};
+  size_t norm_off = 0, gram_off = 0;
+  int norm_stride = 0, gram_stride = 0;      // doubles per device slot
   double * mc_out[SPB200_MAXN] = {nullptr};
+  double * mc_mats[SPB200_MAXN] = {nullptr}; // multicast addresses of the factor replicas
+  double * mc_norms = nullptr;               // k slots of partial column norms
+  double * mc_grams = nullptr;               // k slots of partial Grams
   uint32_t * mc_flag = nullptr;
   uint32_t epoch = 0;
   DevState d[kMaxDev];
@@ -271,10 +293,20 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
   const int k = h->k, N = h->N;
   int devs[kMaxDev];
   for (int i = 0; i < k; ++i) devs[i] = h->d[i].dev;
-  // multicast region: [flags 4 KB][out mode 0][out mode 1]...
+  // multicast region: [flags 4 KB][k norm slots][k Gram slots][out mode 0..][factor mode 0..]
   size_t off = 4096;
+  h->norm_stride = (h->R + 15) / 16 * 16;
+  h->gram_stride = h->R * h->R;
+  h->norm_off = off;
+  off += round_up((size_t)k * h->norm_stride * 8, 4096);
+  h->gram_off = off;
+  off += round_up((size_t)k * h->gram_stride * 8, 4096);
   for (int m = 0; m < N; ++m) {
     h->out_off[m] = off;
+    off += round_up(h->dims[m] * (size_t)h->ldm * 8, 4096);
+  }
+  for (int m = 0; m < N; ++m) {
+    h->mat_off[m] = off;
     off += round_up(h->dims[m] * (size_t)h->ldm * 8, 4096);
   }
   const char * me = getenv("SPLATT_B200_MULTICAST");
@@ -289,16 +321,21 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
     MCK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_r, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
-    for (int m = 0; m < N; ++m) {
-      MCK(cudaMalloc(&s.mats[m], h->dims[m] * (size_t)h->ldm * 8));
-      MCK(cudaMemset(s.mats[m], 0, h->dims[m] * (size_t)h->ldm * 8));
-    }
     if (h->multicast) {
       char * base = reinterpret_cast<char *>(h->mc.uc[i]);
       MCK(cudaMemset(base, 0, h->mc.bytes));
       s.flag_local = reinterpret_cast<uint32_t *>(base);
-      for (int m = 0; m < N; ++m) s.out[m] = reinterpret_cast<double *>(base + h->out_off[m]);
+      s.norms_local = reinterpret_cast<double *>(base + h->norm_off);
+      s.grams_local = reinterpret_cast<double *>(base + h->gram_off);
+      for (int m = 0; m < N; ++m) {
+        s.out[m] = reinterpret_cast<double *>(base + h->out_off[m]);
+        s.mats[m] = reinterpret_cast<double *>(base + h->mat_off[m]);   // replicas live in the region
+      }
     } else {
+      for (int m = 0; m < N; ++m) {
+        MCK(cudaMalloc(&s.mats[m], h->dims[m] * (size_t)h->ldm * 8));
+        MCK(cudaMemset(s.mats[m], 0, h->dims[m] * (size_t)h->ldm * 8));
+      }
       MCK(cudaMalloc(&s.part, h->maxdim * (size_t)h->ldm * 8));
       for (int m = 0; m < N; ++m) MCK(cudaMalloc(&s.out[m], h->dims[m] * (size_t)h->ldm * 8));
     }
@@ -307,7 +344,12 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
   if (h->multicast) {
     char * mb = reinterpret_cast<char *>(h->mc.mc);
     h->mc_flag = reinterpret_cast<uint32_t *>(mb);
-    for (int m = 0; m < N; ++m) h->mc_out[m] = reinterpret_cast<double *>(mb + h->out_off[m]);
+    h->mc_norms = reinterpret_cast<double *>(mb + h->norm_off);
+    h->mc_grams = reinterpret_cast<double *>(mb + h->gram_off);
+    for (int m = 0; m < N; ++m) {
+      h->mc_out[m] = reinterpret_cast<double *>(mb + h->out_off[m]);
+      h->mc_mats[m] = reinterpret_cast<double *>(mb + h->mat_off[m]);
+    }
   }
   if (h->distinct && k > 1) {
     // peer access: the reduce kernel of the fallback reads / writes peer buffers directly, and
@@ -466,7 +508,7 @@ void splatt_b200_multi_free(splatt_b200_multi * h) {
     cudaSetDevice(s.dev);
     if (s.tail) splatt_b200_als_tail_free(s.tail);
     for (int m = 0; m < SPB200_MAXN; ++m) {
-      if (s.mats[m]) cudaFree(s.mats[m]);
+      if (!h->multicast && s.mats[m]) cudaFree(s.mats[m]);
       if (!h->multicast && s.out[m]) cudaFree(s.out[m]);
     }
     if (s.part) cudaFree(s.part);
@@ -647,6 +689,10 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     return SPLATT_ERROR_BADINPUT;
   }
   const int verbosity = (int)options[SPLATT_OPTION_VERBOSITY];
+  // multicast available: the tail is ROW-PARTITIONED over the devices (each solves, normalises
+  // and Grams its own row slice and multicasts it); otherwise one tail on device 0 + pulls
+  const char * pe = getenv("SPLATT_B200_PARTITIONED_TAIL");
+  const bool part = h->multicast && !(pe && atoi(pe) == 0);
   double * mats[SPB200_MAXN] = {nullptr};
   double * lambda = static_cast<double *>(malloc(sizeof(double) * R));
   bool ok = lambda != nullptr;
@@ -673,13 +719,54 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
                               h->dims[m], cudaMemcpyHostToDevice, s.stream);
       if (e != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
     }
-    if (i == 0) {
+    if (i == 0 || part) {
       if (!s.tail) rc = splatt_b200_als_tail_create(N, R, ldm, s.stream, &s.tail);
-      for (int m = 0; m < N && rc == SPLATT_SUCCESS; ++m)
-        rc = splatt_b200_als_tail_gram(s.tail, m, s.mats[m], h->dims[m]);
+      if (!part)
+        for (int m = 0; m < N && rc == SPLATT_SUCCESS; ++m)
+          rc = splatt_b200_als_tail_gram(s.tail, m, s.mats[m], h->dims[m]);
     }
   }
   if (rc != SPLATT_SUCCESS) return fail(rc);
+  // one group barrier on every device's stream (multicast path)
+  auto group_barrier = [&]() -> int {
+    ++h->epoch;
+    for (int i = 0; i < k; ++i) {
+      DevState & s = h->d[i];
+      if (cudaSetDevice(s.dev) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+      k_group_barrier<<<1, 32, 0, s.stream>>>(h->mc_flag, s.flag_local, h->epoch * (uint32_t)k);
+      if (cudaGetLastError() != cudaSuccess) return SPLATT_ERROR_BADINPUT;
+      spb200_count_launches(1);
+    }
+    return SPLATT_SUCCESS;
+  };
+  auto slice = [&](int m, int i, uint64_t * r0, uint64_t * r1) {
+    *r0 = h->dims[m] * (uint64_t)i / k;
+    *r1 = h->dims[m] * (uint64_t)(i + 1) / k;
+  };
+  if (part) {
+    // initial Grams: per-device partials of the row slices, summed in device order everywhere
+    for (int m = 0; m < N; ++m) {
+      for (int i = 0; i < k; ++i) {
+        DevState & s = h->d[i];
+        uint64_t r0, r1;
+        slice(m, i, &r0, &r1);
+        if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        rc = spb200_tail_gram_partial(s.tail, s.mats[m] + r0 * ldm, r1 - r0,
+                                      h->mc_grams + (size_t)i * h->gram_stride);
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+      }
+      rc = group_barrier();
+      if (rc != SPLATT_SUCCESS) return fail(rc);
+      for (int i = 0; i < k; ++i) {
+        DevState & s = h->d[i];
+        if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+        rc = spb200_tail_finish_gram(s.tail, m, s.grams_local, k, h->gram_stride);
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+      }
+      rc = group_barrier();      // the slots may be overwritten from here on
+      if (rc != SPLATT_SUCCESS) return fail(rc);
+    }
+  }
 
   const double ttnormsq = spb200_csf_frobsq(tensors);
   const uint64_t niters = (uint64_t)options[SPLATT_OPTION_NITER];
@@ -689,6 +776,49 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     for (int m = 0; m < N; ++m) {
       rc = multi_mttkrp_enqueue(h, m);
       if (rc != SPLATT_SUCCESS) return fail(rc);
+      if (part) {
+        // every device: solve its row slice, publish its partial column norms ...
+        for (int i = 0; i < k; ++i) {
+          DevState & s = h->d[i];
+          uint64_t r0, r1;
+          slice(m, i, &r0, &r1);
+          if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+          rc = spb200_tail_solve_norm_partial(s.tail, m, s.out[m] + r0 * ldm, s.mats[m] + r0 * ldm,
+                                              r1 - r0, it == 0 ? 1 : 0,
+                                              h->mc_norms + (size_t)i * h->norm_stride);
+          if (rc != SPLATT_SUCCESS) return fail(rc);
+        }
+        rc = group_barrier();
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+        // ... normalise it with the group's lambda, multicast it into every replica, publish
+        // its partial Gram ...
+        for (int i = 0; i < k; ++i) {
+          DevState & s = h->d[i];
+          uint64_t r0, r1;
+          slice(m, i, &r0, &r1);
+          if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+          rc = spb200_tail_scale_gram_partial(s.tail, s.mats[m] + r0 * ldm, h->mc_mats[m] + r0 * ldm,
+                                              r1 - r0, it == 0 ? 1 : 0, s.norms_local, k,
+                                              h->norm_stride, h->mc_grams + (size_t)i * h->gram_stride);
+          if (rc != SPLATT_SUCCESS) return fail(rc);
+        }
+        rc = group_barrier();
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+        // ... and sum the partial Grams in device order: identical factors, lambda and Grams
+        // on every device; the next group exchange (the next mode's kernel) orders the reads of
+        // the slots before their next writes
+        for (int i = 0; i < k; ++i) {
+          DevState & s = h->d[i];
+          if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);
+          rc = spb200_tail_finish_gram(s.tail, m, s.grams_local, k, h->gram_stride);
+          if (rc != SPLATT_SUCCESS) return fail(rc);
+          if (!(m == N - 1 && i == 0)) {        // device 0 still needs the last M1 for the fit
+            rc = multi_release(h, i, m);
+            if (rc != SPLATT_SUCCESS) return fail(rc);
+          }
+        }
+        continue;
+      }
       // device 0: the tail; everybody else: result consumed, wait for the new factor, pull it
       {
         DevState & s0 = h->d[0];

@@ -82,3 +82,35 @@ def test_csf_to_coo_expands_reference_csfs(lib, refmod, spec, tile, alloc):
         got = sorted(zip(*[a.tolist() for a in out], ov.tolist()))
         want = sorted(zip(*[i.tolist() for i in inds], vals.tolist()))
         assert got == want
+
+
+@pytest.mark.parametrize("env,want", [
+    ({}, []),
+    ({"SPLATT_B200_NGPUS": "1"}, []),
+    ({"SPLATT_B200_NGPUS": "4"}, [0, 1, 2, 3]),
+    ({"SPLATT_B200_DEVICES": "0,2,5"}, [0, 2, 5]),
+    ({"SPLATT_B200_DEVICES": "0,0", "SPLATT_B200_NGPUS": "8"}, [0, 0]),     # the list wins
+    ({"SPLATT_B200_NGPUS": "99"}, list(range(16))),                          # capped
+])
+def test_multi_gpu_device_list_from_environment(lib, monkeypatch, env, want):
+    """SPLATT_B200_NGPUS / SPLATT_B200_DEVICES: which devices the drop-in symbols drive from one
+    process (multi.cu); no variable or one device = the single-GPU path."""
+    for k in ("SPLATT_B200_NGPUS", "SPLATT_B200_DEVICES"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    buf = (C.c_int * 16)()
+    n = lib.splatt_b200_multi_env_devices(buf, 16)
+    assert [buf[i] for i in range(n)] == want
+
+
+def test_multi_gpu_engine_rejects_bad_arguments(lib):
+    """No GPU needed: argument checks come before any CUDA call."""
+    out = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    assert lib.splatt_b200_multi_create(None, 1, 8, devs, 1, 0, C.byref(out)) == A.SPLATT_ERROR_BADINPUT
+    assert lib.splatt_b200_multi_mttkrp_host(None, 0, None, None) == A.SPLATT_ERROR_BADINPUT
+    assert lib.splatt_b200_multi_info(None, None, None, None, None) == A.SPLATT_ERROR_BADINPUT
+    lib.splatt_b200_multi_free(None)
+    lib.splatt_b200_cache_clear()                       # empty cache: a no-op
+    assert lib.splatt_b200_build_count() == 0

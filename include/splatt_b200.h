@@ -371,16 +371,21 @@ int splatt_b200_mttkrp_multicast(
     void * stream);
 
 /* The same with the group barrier folded into the kernel's tail (no separate barrier
- * launch): `sync->mc_flag` is the multicast address and `sync->local_flag` this GPU's own
- * address of one uint32 in the group's symmetric memory (zero before first use);
- * `sync->target` = (number of barrier launches so far, including this one) x group size --
- * the caller counts.  When the kernel completes on a GPU, every peer's reductions have
- * landed in that GPU's buffer.  All GPUs of the group must launch (an empty shard too). */
+ * launch).  The group owns an array of `world` (<= 64) uint32 flags in its symmetric /
+ * multicast memory, zero before first use: `sync->mc_flag` is the array's multicast address,
+ * `sync->local_flag` this GPU's own address of it.  `sync->target` is the barrier's sequence
+ * number (1, 2, 3, ... -- the caller counts; every GPU of the group passes the same number),
+ * `rank` / `world` this GPU's slot and the group size.  The last CTA of the kernel stores the
+ * number into its slot on every GPU and waits until all slots of the local copy hold it; when
+ * the kernel completes on a GPU, every peer's reductions have landed in that GPU's buffer.
+ * All GPUs of the group must launch (an empty shard too). */
 typedef struct
 {
   uint32_t * mc_flag;
   uint32_t * local_flag;
   uint32_t   target;
+  uint32_t   rank;
+  uint32_t   world;
   uint32_t   reserved;
 } splatt_b200_group_sync;
 int splatt_b200_mttkrp_multicast_sync(

@@ -1,5 +1,6 @@
 """Quick device-side timing of the MTTKRP kernels on a synthetic uniform tensor.
 usage: python scripts/quick_bench.py [dim] [nnz] [R] [nmodes] [layout]"""
+import os
 import sys
 import time
 
@@ -17,6 +18,9 @@ layout = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 
 g = torch.Generator(device="cuda").manual_seed(1)
 dims = [dim] * N
+if os.environ.get("DIMS"):                      # e.g. DIMS=10000,10000,64 (long fibers)
+    dims = [int(x) for x in os.environ["DIMS"].split(",")]
+    N = len(dims)
 if len(sys.argv) > 6 and sys.argv[6] == "zipf":
     # config-5 shape family: dim x dim x 1000, Zipf(1.0) on the two long modes
     dims = [dim, dim, 1000]
@@ -30,10 +34,9 @@ if len(sys.argv) > 6 and sys.argv[6] == "zipf":
         return perm[r].to(torch.int32)
     ind = [zipf(dim), zipf(dim), torch.randint(0, 1000, (nnz,), device="cuda", dtype=torch.int32, generator=g)]
 else:
-    ind = [torch.randint(0, dim, (nnz,), device="cuda", dtype=torch.int32, generator=g) for _ in range(N)]
+    ind = [torch.randint(0, d, (nnz,), device="cuda", dtype=torch.int32, generator=g) for d in dims]
 vals = torch.rand(nnz, device="cuda", dtype=torch.float64, generator=g)
 t0 = time.time()
-import os
 T = S.Tensor.from_coo(dims, ind, vals, layout=layout, csf_alloc=int(os.environ.get("CSF_ALLOC", "1")), verbosity=3,
                       ncolumns_hint=R, ktile=int(os.environ.get("KTILE", "-1")))
 torch.cuda.synchronize()

@@ -84,7 +84,7 @@ class BuildOpts(C.Structure):
 
 class GroupSync(C.Structure):
     _fields_ = [("mc_flag", C.c_void_p), ("local_flag", C.c_void_p), ("target", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("rank", C.c_uint32), ("world", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 LIB_PATH = Path(__file__).resolve().parent / "libsplatt_b200.so"

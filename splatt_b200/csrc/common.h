@@ -114,13 +114,15 @@ struct MttkrpArgs {
   int              rpad, apad; // shared-memory stagger: pad records / pad ids per group region (0 = none)
   // Group barrier folded into the kernel's tail (multicast launches only; null = off):
   // after its last row reduction every CTA fences at system scope; the last CTA to finish
-  // adds 1 to the group's flag on EVERY GPU (multimem.red on sync_mc) and spins on this
-  // GPU's copy until it reaches sync_target (= launches so far x group size).  When the
-  // kernel exits, every peer's reductions have landed in this GPU's output buffer.
+  // stores sync_target (the barrier's sequence number) into THIS GPU's slot of the group's
+  // flag array on EVERY GPU (multimem.st on sync_mc + sync_rank) and spins on this GPU's copy
+  // until all sync_world slots have reached it.  When the kernel exits, every peer's
+  // reductions have landed in this GPU's output buffer.
   uint32_t *       sync_mc;
   uint32_t *       sync_local;
   uint32_t *       sync_cta;   // this GPU's finished-CTA counter (device memory, starts at 0)
   uint32_t         sync_target;
+  uint32_t         sync_rank, sync_world;
 };
 
 // Host-side description of the group barrier (see MttkrpArgs).
@@ -129,6 +131,7 @@ struct GroupSync {
   uint32_t * local_flag = nullptr;
   uint32_t * cta_done = nullptr;
   uint32_t   target = 0;
+  uint32_t   rank = 0, world = 1;
 };
 
 #define SPB200_CUDA_OK(call)                                                   \

@@ -737,7 +737,9 @@ struct DevTail {
   // G += A^T A (G is NOT zeroed here)
   void gram_into(const double * A, uint64_t I, double * G) {
     if (I == 0) return;
-    if (rt) {
+    // the persistent SYRK pays one round of atomics per CTA: worth it from ~32 K rows on
+    // (measured: 10 K x 32: 22.6 us vs 13.3 us generic; 1 M x 64: 0.74 ms vs 1.2 ms)
+    if (rt && I >= 32768) {
       const unsigned blocks = (unsigned)std::min<uint64_t>((I + 63) / 64, 296);
       const size_t sm = (size_t)64 * rt * 8;
       if (rt == 16) k_gram_syrk<16><<<blocks, 64, sm, s>>>(A, I, R, ld, G);

@@ -556,6 +556,11 @@ int splatt_b200_mttkrp_multicast_sync(splatt_b200_tensor const * t, int mode, in
   GroupSync gs;
   gs.mc_flag = sync->mc_flag; gs.local_flag = sync->local_flag; gs.cta_done = t->cta_done;
   gs.target = sync->target;
+  gs.rank = sync->rank; gs.world = sync->world;
+  if (gs.world < 1 || gs.world > 64 || gs.rank >= gs.world) {
+    fprintf(stderr, "SPLATT: splatt_b200_mttkrp_multicast_sync: bad rank/world (%u/%u)\n", gs.rank, gs.world);
+    return SPLATT_ERROR_BADINPUT;
+  }
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
                               mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true, 0, 0,
                               &gs);

@@ -125,6 +125,20 @@ __device__ __forceinline__ void red_row_mc(char * __restrict__ base, uint32_t id
   asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(x.x) : "memory");
   asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(x.y) : "memory");
 }
+// Group barrier primitive: GPU `rank` of `world` publishes `epoch` in ITS OWN slot of the
+// group's flag array on every GPU (one multicast store), then waits until every slot of the
+// local copy has reached `epoch`.  One slot per GPU (not an arrival count): a fast GPU's next
+// arrival can never stand in for a slow GPU's current one.
+__device__ __forceinline__ void group_signal_and_wait(uint32_t * mc_flags, uint32_t * local_flags,
+                                                      uint32_t epoch, uint32_t rank, uint32_t world) {
+  asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_flags + rank), "r"(epoch) : "memory");
+  for (uint32_t r = 0; r < world; ++r) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flags + r) : "memory");
+    } while (static_cast<int>(v - epoch) < 0);
+  }
+}
 __device__ __forceinline__ double2 fma2(double s, double2 a, double2 c) {
   return make_double2(fma(s, a.x, c.x), fma(s, a.y, c.y));
 }
@@ -473,12 +487,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
         if (done == gridDim.x - 1) {          // last CTA of this GPU
           *reinterpret_cast<volatile unsigned int *>(a.sync_cta) = 0u;   // ready for the next launch
           __threadfence_system();
-          asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;"
-                       ::"l"(a.sync_mc), "r"(1u) : "memory");
-          unsigned int v;
-          do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.sync_local) : "memory");
-          } while (static_cast<int>(v - a.sync_target) < 0);
+          group_signal_and_wait(a.sync_mc, a.sync_local, a.sync_target, a.sync_rank, a.sync_world);
         }
       }
     }

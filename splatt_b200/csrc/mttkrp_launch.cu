@@ -134,6 +134,7 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
   a.multicast = multicast_out ? 1 : 0;
   a.sync_mc = a.sync_local = a.sync_cta = nullptr;
   a.sync_target = 0;
+  a.sync_rank = 0; a.sync_world = 1;
   {
     // SPLATT_B200_STAGGER: 0 = aligned regions (bank conflicts on the broadcast reads),
     // 1 = stagger the record regions, 2 = records and ancestor ids
@@ -153,6 +154,7 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
     if (multicast_out && sync && c0 + 64 >= col_end) {     // the last column pass carries the barrier
       a.sync_mc = sync->mc_flag; a.sync_local = sync->local_flag; a.sync_cta = sync->cta_done;
       a.sync_target = sync->target;
+      a.sync_rank = sync->rank; a.sync_world = sync->world;
     }
     int rc;
     switch (N) {

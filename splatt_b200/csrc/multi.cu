@@ -218,17 +218,24 @@ __global__ void k_peer_reduce(const PeerReduceArgs a, unsigned long long e0, uns
   }
 }
 
-// Stand-alone group barrier (same flag and arrival count as the MTTKRP kernel's tail): the
-// kernels before it on this stream have completed, so their multicast stores are performed;
-// signal every GPU, wait until every GPU has signalled.
-__global__ void k_group_barrier(uint32_t * mc_flag, uint32_t * local_flag, uint32_t target) {
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flag), "r"(1u) : "memory");
+// Stand-alone group barrier (same flag array and sequence numbers as the MTTKRP kernel's
+// tail): the kernels before it on this stream have completed, so their multicast stores are
+// performed; publish the sequence number in this GPU's slot on every GPU, wait for all slots.
+__device__ __forceinline__ void mg_signal_and_wait(uint32_t * mc_flags, uint32_t * local_flags,
+                                                   uint32_t epoch, uint32_t rank, uint32_t world) {
+  asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_flags + rank), "r"(epoch) : "memory");
+  for (uint32_t r = 0; r < world; ++r) {
     unsigned int v;
     do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flag) : "memory");
-    } while (static_cast<int>(v - target) < 0);
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flags + r) : "memory");
+    } while (static_cast<int>(v - epoch) < 0);
+  }
+}
+__global__ void k_group_barrier(uint32_t * mc_flags, uint32_t * local_flags, uint32_t epoch,
+                                uint32_t rank, uint32_t world) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    mg_signal_and_wait(mc_flags, local_flags, epoch, rank, world);
   }
 }
 
@@ -385,7 +392,9 @@ int multi_mttkrp_enqueue(splatt_b200_multi * h, int mode) {
       splatt_b200_group_sync gs;
       gs.mc_flag = h->mc_flag;
       gs.local_flag = s.flag_local;
-      gs.target = h->epoch * (uint32_t)k;
+      gs.target = h->epoch;
+      gs.rank = (uint32_t)i;
+      gs.world = (uint32_t)k;
       gs.reserved = 0;
       int rc = splatt_b200_mttkrp_multicast_sync(s.T, mode, h->R, h->ldm, s.mats, h->mc_out[mode],
                                                  &gs, s.stream);
@@ -733,7 +742,8 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     for (int i = 0; i < k; ++i) {
       DevState & s = h->d[i];
       if (cudaSetDevice(s.dev) != cudaSuccess) return SPLATT_ERROR_BADINPUT;
-      k_group_barrier<<<1, 32, 0, s.stream>>>(h->mc_flag, s.flag_local, h->epoch * (uint32_t)k);
+      k_group_barrier<<<1, 32, 0, s.stream>>>(h->mc_flag, s.flag_local, h->epoch, (uint32_t)i,
+                                              (uint32_t)k);
       if (cudaGetLastError() != cudaSuccess) return SPLATT_ERROR_BADINPUT;
       spb200_count_launches(1);
     }

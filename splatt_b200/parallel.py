@@ -64,6 +64,7 @@ class FusedExchange:
         self.ldm = ncolumns + (ncolumns & 1)
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
         if kernel_barrier is None:
             kernel_barrier = os.environ.get("SPLATT_B200_KERNEL_BARRIER", "1") != "0"
         self.kernel_barrier = bool(kernel_barrier)
@@ -124,7 +125,7 @@ class FusedExchange:
         if self.kernel_barrier:
             self._epoch += 1
             gs = A.GroupSync(self.flags_hdl.multicast_ptr, self.flags.data_ptr(),
-                             (self._epoch * self.world) & 0xffffffff, 0)
+                             self._epoch & 0xffffffff, self.rank, self.world, 0)
             rc = lib.splatt_b200_mttkrp_multicast_sync(self.t.h, mode, self.R, self.ldm, ptrs,
                                                        mc_out, C.byref(gs), C.c_void_p(s))
             if rc != A.SPLATT_SUCCESS:

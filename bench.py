@@ -539,6 +539,23 @@ class Workload:
                    for m in range(self.N)]
         return step_ms, mode_ms, wall
 
+    def keep_busy(self, flush, seconds):
+        """The same sweep loop, untimed, for `seconds`: gives the 100 ms clock sampler a window
+        under this workload (the timed region itself is only tens of milliseconds long)."""
+        import torch
+        t0 = time.time()
+        while True:
+            for _ in range(20):
+                flush.zero_()
+                self.sweep()
+            torch.cuda.synchronize()
+            stop = torch.tensor([1.0 if time.time() - t0 >= seconds else 0.0], device=self.ctx.dev)
+            if self.ctx.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(stop, op=dist.ReduceOp.MAX)      # every rank leaves together
+            if stop.item() > 0.5:
+                break
+
     def free(self):
         import torch
         self.T.free()
@@ -589,6 +606,7 @@ def run_named(ctx, key, args, flush):
     step_ms, mode_ms, _ = wl.timed(flush, steps, max(args.warmup, 3))
     ms_per_step = ctx.max_over_ranks(float(np.sum(step_ms))) / steps
     per_mode = [ctx.max_over_ranks(float(np.mean(mode_ms[m]))) for m in range(wl.N)]
+    wl.keep_busy(flush, 0.5)
     clocks = sampler.stop() if sampler else None
     par = parity_vs_reference(ctx, f"named{key}", dims, ind_h, vals_h, wl.mats_h, ours)
     rec = None
@@ -686,7 +704,12 @@ def run_ours(args):
     worst_step = ctx.max_over_ranks(float(np.max(step_ms)))
     best_step = ctx.max_over_ranks(float(np.min(step_ms)))
     value = nnz_total * RANK * NMODES / (ms_per_step * 1e-3)
+    wl.keep_busy(flush, 1.0)               # clock samples under this very workload
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = ("build + warm-up + timed region + 1 s of the same sweep loop right "
+                            "after it (the timed region alone is shorter than the 100 ms "
+                            "sampling period)")
     ind_h = vals_h = None
     if rank == 0:
         ind_h = [i.cpu().numpy().astype(np.uint64) for i in ind]

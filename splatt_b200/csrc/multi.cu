@@ -753,6 +753,19 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     *r0 = h->dims[m] * (uint64_t)i / k;
     *r1 = h->dims[m] * (uint64_t)(i + 1) / k;
   };
+  // SPLATT_B200_MULTI_TIMING=1: synchronise all devices after every phase and report where an
+  // iteration's wall time goes (diagnostics; it serialises the phases)
+  const char * te = getenv("SPLATT_B200_MULTI_TIMING");
+  const bool timing = te && atoi(te) != 0;
+  double tphase[5] = {0, 0, 0, 0, 0};
+  auto tmark = std::chrono::steady_clock::now();
+  auto phase_done = [&](int ph) {
+    if (!timing) return;
+    for (int i = 0; i < k; ++i) { cudaSetDevice(h->d[i].dev); cudaStreamSynchronize(h->d[i].stream); }
+    auto now = std::chrono::steady_clock::now();
+    tphase[ph] += std::chrono::duration<double, std::milli>(now - tmark).count();
+    tmark = now;
+  };
   if (part) {
     // initial Grams: per-device partials of the row slices, summed in device order everywhere
     for (int m = 0; m < N; ++m) {
@@ -784,8 +797,10 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
   for (uint64_t it = 0; it < niters; ++it) {
     auto t0 = std::chrono::steady_clock::now();
     for (int m = 0; m < N; ++m) {
+      if (timing) { phase_done(4); }
       rc = multi_mttkrp_enqueue(h, m);
       if (rc != SPLATT_SUCCESS) return fail(rc);
+      phase_done(0);
       if (part) {
         // every device: solve its row slice, publish its partial column norms ...
         for (int i = 0; i < k; ++i) {
@@ -800,6 +815,7 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
         }
         rc = group_barrier();
         if (rc != SPLATT_SUCCESS) return fail(rc);
+        phase_done(1);
         // ... normalise it with the group's lambda, multicast it into every replica, publish
         // its partial Gram ...
         for (int i = 0; i < k; ++i) {
@@ -814,6 +830,7 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
         }
         rc = group_barrier();
         if (rc != SPLATT_SUCCESS) return fail(rc);
+        phase_done(2);
         // ... and sum the partial Grams in device order: identical factors, lambda and Grams
         // on every device; the next group exchange (the next mode's kernel) orders the reads of
         // the slots before their next writes
@@ -827,6 +844,7 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
             if (rc != SPLATT_SUCCESS) return fail(rc);
           }
         }
+        phase_done(3);
         continue;
       }
       // device 0: the tail; everybody else: result consumed, wait for the new factor, pull it
@@ -870,6 +888,10 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     if (fit == 1. || (it > 0 && std::fabs(fit - oldfit) < options[SPLATT_OPTION_TOLERANCE])) break;
     oldfit = fit;
   }
+  if (timing)
+    printf("SPLATT-B200: multi CPD phases (ms, all iterations): mttkrp %.2f | solve+norm %.2f | "
+           "scale+gram %.2f | gram sum+release %.2f | fit/other %.2f\n",
+           tphase[0], tphase[1], tphase[2], tphase[3], tphase[4]);
   // factors back from device 0 (replicas agree to rounding)
   {
     DevState & s = h->d[0];

@@ -876,7 +876,8 @@ def run_ours(args):
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(n_gpus), exchange=exchange),
+                "config": workload_config(n_gpus),      # identical in both arms
+                "exchange": exchange,
                 "clocks": clocks,
                 "parity_rel_fro": parity.get("per_mode") if parity else None, "parity": parity,
                 "step_ms_min": best_step, "step_ms_max": worst_step,
@@ -896,9 +897,13 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         if world > 1:
-            time.sleep(1.0)          # let the other ranks' NCCL teardown lines out first
+            time.sleep(2.0)          # let the other ranks' NCCL teardown lines out first
         sys.stdout.flush()
+        sys.stderr.flush()
         print(json.dumps(line), flush=True)
+        # the JSON line must be the LAST line on stdout: with NCCL_DEBUG=INFO the library
+        # prints from its exit handlers ("Closing env plugin ...") -- leave without running them
+        os._exit(0)
     return 0
 
 

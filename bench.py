@@ -868,7 +868,7 @@ def run_ours(args):
                                c_abi_multicast=mg.multicast,
                                c_abi_path=f"splatt_b200_multi_cpd_als on {world} GPUs (what "
                                           "splatt_cpd_als runs with SPLATT_B200_NGPUS set): "
-                                          "single-process multi-GPU engine, tail on device 0")
+                                          "single-process multi-GPU engine, row-partitioned tail")
                     mg.free()
             except Exception as e:  # pragma: no cover
                 cpd = dict(cpd_multi or {}, error=f"{type(e).__name__}: {e}")

@@ -68,6 +68,10 @@ static int launch_kind(int kind, const MttkrpArgs & args, int num_sms, cudaStrea
           return launch_variant<N, L, SPB200_KIND_ROOT, 2, false, false, 4>(args, num_sms, stream);
         if (spb200_root_batch() == 4 && spb200_root_minb() == 4)
           return launch_variant<N, L, SPB200_KIND_ROOT, 4, false, false, 4>(args, num_sms, stream);
+        if (spb200_root_batch() == 3 && spb200_root_minb() == 4)
+          return launch_variant<N, L, SPB200_KIND_ROOT, 3, false, false, 4>(args, num_sms, stream);
+        if (spb200_root_batch() == 3 && spb200_root_minb() == 3)
+          return launch_variant<N, L, SPB200_KIND_ROOT, 3, false, false, 3>(args, num_sms, stream);
       }
       // deeper trees hold a third gathered row per record: two-record batches keep the
       // kernel at 80 registers / 3 CTAs per SM (measured 1014 vs 1052 us on config 3)

@@ -325,6 +325,10 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
     DevState & s = h->d[i];
     MCK(cudaSetDevice(s.dev));
     MCK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (s.T && !s.T->cta_done) {     // scratch of the in-kernel barrier: not lazily, later launches
+      MCK(cudaMalloc(&s.T->cta_done, 64));   // come from one host thread per device
+      MCK(cudaMemset(s.T->cta_done, 0, 64));
+    }
     MCK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_r, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
@@ -383,24 +387,44 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
 
 // One MTTKRP over all devices; on return (in stream order of every device) out[d][mode]
 // holds the full sum on every device.
+// The fused kernel of device i for barrier sequence number `epoch`.
+int enqueue_mc_device(splatt_b200_multi * h, int i, int mode, uint32_t epoch) {
+  DevState & s = h->d[i];
+  splatt_b200_group_sync gs;
+  gs.mc_flag = h->mc_flag;
+  gs.local_flag = s.flag_local;
+  gs.target = epoch;
+  gs.rank = (uint32_t)i;
+  gs.world = (uint32_t)h->k;
+  gs.reserved = 0;
+  return splatt_b200_mttkrp_multicast_sync(s.T, mode, h->R, h->ldm, s.mats, h->mc_out[mode], &gs,
+                                           s.stream);
+}
+
+// In the multicast path nothing orders the devices on the host (the barriers are on the
+// devices), so every device gets its own host thread for the enqueue: with 8 devices the
+// ~10 API calls per device and mode otherwise add up to the duration of the kernels.
+// All host-side parallel regions of this file use ONE team size: libgomp re-creates threads
+// when consecutive regions ask for different team sizes (measured: 16-thread staging copies
+// alternating with 2-thread device regions cost 0.3-0.4 ms per switch).
+constexpr int kHostTeam = 16;
+
+template <class F>
+int for_each_device_parallel(int k, F f) {
+  int rc_all = SPLATT_SUCCESS;
+#pragma omp parallel for num_threads(kHostTeam) schedule(static, 1) reduction(max : rc_all)
+  for (int i = 0; i < k; ++i) {
+    const int r = f(i);
+    if (r != SPLATT_SUCCESS && r > rc_all) rc_all = r;
+  }
+  return rc_all;
+}
+
 int multi_mttkrp_enqueue(splatt_b200_multi * h, int mode) {
   const int k = h->k;
   if (h->multicast) {
-    ++h->epoch;
-    for (int i = 0; i < k; ++i) {
-      DevState & s = h->d[i];
-      splatt_b200_group_sync gs;
-      gs.mc_flag = h->mc_flag;
-      gs.local_flag = s.flag_local;
-      gs.target = h->epoch;
-      gs.rank = (uint32_t)i;
-      gs.world = (uint32_t)k;
-      gs.reserved = 0;
-      int rc = splatt_b200_mttkrp_multicast_sync(s.T, mode, h->R, h->ldm, s.mats, h->mc_out[mode],
-                                                 &gs, s.stream);
-      if (rc != SPLATT_SUCCESS) return rc;
-    }
-    return SPLATT_SUCCESS;
+    const uint32_t epoch = ++h->epoch;
+    return for_each_device_parallel(k, [&](int i) { return enqueue_mc_device(h, i, mode, epoch); });
   }
   // fallback: local partials, then the peer reduce
   for (int i = 0; i < k; ++i) {
@@ -464,7 +488,7 @@ bool host_pinned(const void * p, size_t bytes) {
 void par_memcpy(void * dst, const void * src, size_t bytes) {
   const size_t chunk = 1 << 17;
   const int64_t n = (int64_t)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) num_threads(16)
+#pragma omp parallel for schedule(static) num_threads(kHostTeam)
   for (int64_t c = 0; c < n; ++c) {
     const size_t o = (size_t)c * chunk;
     memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, std::min(chunk, bytes - o));
@@ -640,22 +664,23 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
       src[m] = h->stage_in + off;
       off += h->dims[m] * J;
     }
-    // issue this matrix to every device as soon as it is staged (k PCIe links in parallel)
-    for (int i = 0; i < k; ++i) {
+    // issue this matrix to every device as soon as it is staged (k PCIe links in parallel,
+    // one host thread per device)
+    const int rcm = for_each_device_parallel(k, [&](int i) -> int {
       DevState & s = h->d[i];
-      MCK(cudaSetDevice(s.dev));
-      if (ld == J)
-        MCK(cudaMemcpyAsync(s.mats[m], src[m], h->dims[m] * J * 8, cudaMemcpyHostToDevice, s.stream));
-      else
-        MCK(cudaMemcpy2DAsync(s.mats[m], ld * 8, src[m], J * 8, J * 8, h->dims[m],
-                              cudaMemcpyHostToDevice, s.stream));
-    }
+      cudaError_t e = cudaSetDevice(s.dev);
+      if (e == cudaSuccess)
+        e = (ld == J) ? cudaMemcpyAsync(s.mats[m], src[m], h->dims[m] * J * 8, cudaMemcpyHostToDevice, s.stream)
+                      : cudaMemcpy2DAsync(s.mats[m], ld * 8, src[m], J * 8, J * 8, h->dims[m],
+                                          cudaMemcpyHostToDevice, s.stream);
+      return e == cudaSuccess ? SPLATT_SUCCESS : SPLATT_ERROR_BADINPUT;
+    });
+    if (rcm != SPLATT_SUCCESS) return rcm;
   }
   double * dst_host = pinned ? out_host : h->stage_out;
-  int rc = multi_mttkrp_enqueue(h, mode);
-  if (rc != SPLATT_SUCCESS) return rc;
   const uint64_t I = h->dims[mode];
-  for (int i = 0; i < k; ++i) {
+  int rc = SPLATT_SUCCESS;
+  auto tail_of_device = [&](int i) -> int {       // result slice back + buffer ready for its next use
     DevState & s = h->d[i];
     MCK(cudaSetDevice(s.dev));
     const uint64_t r0 = I * i / k, r1 = I * (i + 1) / k;
@@ -667,8 +692,23 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
         MCK(cudaMemcpy2DAsync(dst_host + r0 * J, J * 8, s.out[mode] + r0 * ld, ld * 8, J * 8, r1 - r0,
                               cudaMemcpyDeviceToHost, s.stream));
     }
-    rc = multi_release(h, i, mode);
+    return multi_release(h, i, mode);
+  };                                              // enqueue only: never block inside the region
+                                                  // (a thread may serve several devices)
+  if (h->multicast) {
+    const uint32_t epoch = ++h->epoch;
+    rc = for_each_device_parallel(k, [&](int i) -> int {
+      const int r = enqueue_mc_device(h, i, mode, epoch);
+      return r == SPLATT_SUCCESS ? tail_of_device(i) : r;
+    });
     if (rc != SPLATT_SUCCESS) return rc;
+  } else {
+    rc = multi_mttkrp_enqueue(h, mode);
+    if (rc != SPLATT_SUCCESS) return rc;
+    for (int i = 0; i < k; ++i) {
+      rc = tail_of_device(i);
+      if (rc != SPLATT_SUCCESS) return rc;
+    }
   }
   for (int i = 0; i < k; ++i) {
     MCK(cudaSetDevice(h->d[i].dev));
@@ -798,11 +838,47 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     auto t0 = std::chrono::steady_clock::now();
     for (int m = 0; m < N; ++m) {
       if (timing) { phase_done(4); }
-      rc = multi_mttkrp_enqueue(h, m);
-      if (rc != SPLATT_SUCCESS) return fail(rc);
-      phase_done(0);
+      if (!(part && !timing)) {
+        rc = multi_mttkrp_enqueue(h, m);
+        if (rc != SPLATT_SUCCESS) return fail(rc);
+        phase_done(0);
+      }
+      if (part && !timing) {
+        // One host thread per device enqueues the device's whole mode step: fused MTTKRP
+        // (barrier e0 in its tail), solve of its row slice + partial column norms -> slot,
+        // barrier e1, lambda from all slots, scale + multicast of the slice, partial Gram ->
+        // slot, barrier e2, Gram = sum of the slots in device order.  Identical factors, lambda
+        // and Grams on every device; the next mode's kernel barrier orders the reads of the
+        // slots before their next writes.  Nothing orders the devices on the host.
+        const uint32_t e0 = ++h->epoch, e1 = ++h->epoch, e2 = ++h->epoch;
+        const int rcp = for_each_device_parallel(k, [&](int i) -> int {
+          DevState & s = h->d[i];
+          uint64_t r0, r1;
+          slice(m, i, &r0, &r1);
+          int r = enqueue_mc_device(h, i, m, e0);
+          if (r != SPLATT_SUCCESS) return r;
+          if (cudaSetDevice(s.dev) != cudaSuccess) return (int)SPLATT_ERROR_BADINPUT;
+          r = spb200_tail_solve_norm_partial(s.tail, m, s.out[m] + r0 * ldm, s.mats[m] + r0 * ldm,
+                                             r1 - r0, it == 0 ? 1 : 0,
+                                             h->mc_norms + (size_t)i * h->norm_stride);
+          if (r != SPLATT_SUCCESS) return r;
+          k_group_barrier<<<1, 32, 0, s.stream>>>(h->mc_flag, s.flag_local, e1, (uint32_t)i, (uint32_t)k);
+          r = spb200_tail_scale_gram_partial(s.tail, s.mats[m] + r0 * ldm, h->mc_mats[m] + r0 * ldm,
+                                             r1 - r0, it == 0 ? 1 : 0, s.norms_local, k,
+                                             h->norm_stride, h->mc_grams + (size_t)i * h->gram_stride);
+          if (r != SPLATT_SUCCESS) return r;
+          k_group_barrier<<<1, 32, 0, s.stream>>>(h->mc_flag, s.flag_local, e2, (uint32_t)i, (uint32_t)k);
+          spb200_count_launches(2);
+          r = spb200_tail_finish_gram(s.tail, m, s.grams_local, k, h->gram_stride);
+          if (r != SPLATT_SUCCESS) return r;
+          if (!(m == N - 1 && i == 0)) r = multi_release(h, i, m);   // device 0 keeps the last M1 for the fit
+          return r;
+        });
+        if (rcp != SPLATT_SUCCESS) return fail(rcp);
+        continue;
+      }
       if (part) {
-        // every device: solve its row slice, publish its partial column norms ...
+        // the same step, phase by phase from one host thread (SPLATT_B200_MULTI_TIMING)
         for (int i = 0; i < k; ++i) {
           DevState & s = h->d[i];
           uint64_t r0, r1;
@@ -816,8 +892,6 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
         rc = group_barrier();
         if (rc != SPLATT_SUCCESS) return fail(rc);
         phase_done(1);
-        // ... normalise it with the group's lambda, multicast it into every replica, publish
-        // its partial Gram ...
         for (int i = 0; i < k; ++i) {
           DevState & s = h->d[i];
           uint64_t r0, r1;
@@ -831,9 +905,6 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
         rc = group_barrier();
         if (rc != SPLATT_SUCCESS) return fail(rc);
         phase_done(2);
-        // ... and sum the partial Grams in device order: identical factors, lambda and Grams
-        // on every device; the next group exchange (the next mode's kernel) orders the reads of
-        // the slots before their next writes
         for (int i = 0; i < k; ++i) {
           DevState & s = h->d[i];
           if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);

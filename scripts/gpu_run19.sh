@@ -1,0 +1,10 @@
+mkdir -p gpurun_out/r2
+timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu -k "host_matches or dropin" > gpurun_out/r2/pytest_multi_2gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2/pytest_multi_2gpu.log
+(time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 --named "") > gpurun_out/r2/bench_n2.out 2> gpurun_out/r2/bench_n2.err; echo "bench rc=$?"
+tail -1 gpurun_out/r2/bench_n2.out > gpurun_out/r2/bench_n2.json
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2/bench_n2.json").read())
+for k in ("value","ms_per_step","parity_rel_fro"): print(k, d.get(k))
+e=d["e2e"]; print("e2e", {k:e.get(k) for k in ("value","ms_per_step","pinned","pageable_over_pinned","error")})
+PY

@@ -407,7 +407,7 @@ int enqueue_mc_device(splatt_b200_multi * h, int i, int mode, uint32_t epoch) {
 // All host-side parallel regions of this file use ONE team size: libgomp re-creates threads
 // when consecutive regions ask for different team sizes (measured: 16-thread staging copies
 // alternating with 2-thread device regions cost 0.3-0.4 ms per switch).
-constexpr int kHostTeam = 32;
+constexpr int kHostTeam = 16;
 
 template <class F>
 int for_each_device_parallel(int k, F f) {
@@ -710,16 +710,12 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
       if (rc != SPLATT_SUCCESS) return rc;
     }
   }
-  // everything is enqueued: now one thread per device may block -- wait for the device and
-  // move its row slice from the bounce buffer into the caller's (pageable) matrix
-  rc = for_each_device_parallel(k, [&](int i) -> int {
+  for (int i = 0; i < k; ++i) {
     MCK(cudaSetDevice(h->d[i].dev));
     MCK(cudaStreamSynchronize(h->d[i].stream));
-    const uint64_t r0 = I * i / k, r1 = I * (i + 1) / k;
-    if (!pinned && r1 > r0) memcpy(out_host + r0 * J, h->stage_out + r0 * J, (r1 - r0) * J * 8);
-    return SPLATT_SUCCESS;
-  });
-  if (rc != SPLATT_SUCCESS) return rc;
+  }
+  // (measured: unstaging per device from k threads, or a 32-thread team, is slower than this)
+  if (!pinned) par_memcpy(out_host, h->stage_out, I * J * 8);
   cudaSetDevice(h->prev_dev);
   h->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return SPLATT_SUCCESS;

@@ -398,6 +398,21 @@ int splatt_b200_mttkrp_multicast_sync(
     splatt_b200_group_sync const * sync,
     void * stream);
 
+/* ... for a block of columns only ([col_begin, col_begin + col_count), col_begin even;
+ * col_count <= 0: all columns): lets a host pipeline column blocks against the PCIe copies of
+ * the factor columns while the exchange stays fused (the multi-GPU engine's host-buffer call). */
+int splatt_b200_mttkrp_multicast_sync_columns(
+    splatt_b200_tensor const * t,
+    int mode,
+    int ncolumns,
+    int ldm,
+    double const * const * d_mats,
+    double * mc_out,
+    int col_begin,
+    int col_count,
+    splatt_b200_group_sync const * sync,
+    void * stream);
+
 /* Cut shard `rank` of `count` out of a WHOLE device tensor (built with shard_count <= 1)
  * onto CUDA device `device` (-1 = the whole tensor's device): the same equal-nnz chunk
  * range splatt_b200_shard_range names, copied device-to-device (P2P) instead of being

@@ -100,6 +100,7 @@ EXPORTS = [
     "splatt_b200_als_tail_create", "splatt_b200_als_tail_free", "splatt_b200_als_tail_gram",
     "splatt_b200_als_tail_update", "splatt_b200_als_tail_fit", "splatt_b200_csf_to_coo",
     "splatt_b200_tensor_shard", "splatt_b200_mttkrp_multicast_sync",
+    "splatt_b200_mttkrp_multicast_sync_columns",
     "splatt_b200_multi_env_devices", "splatt_b200_multi_create", "splatt_b200_multi_free",
     "splatt_b200_multi_info", "splatt_b200_multi_mttkrp_host", "splatt_b200_multi_cpd_als",
     "splatt_b200_multi_last_ms", "splatt_b200_build_count", "splatt_b200_cache_clear",
@@ -197,6 +198,10 @@ def load() -> C.CDLL:
     lib.splatt_b200_mttkrp_multicast_sync.restype = C.c_int
     lib.splatt_b200_mttkrp_multicast_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, vpp,
                                                       val_p, C.POINTER(GroupSync), C.c_void_p]
+    lib.splatt_b200_mttkrp_multicast_sync_columns.restype = C.c_int
+    lib.splatt_b200_mttkrp_multicast_sync_columns.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                              vpp, val_p, C.c_int, C.c_int,
+                                                              C.POINTER(GroupSync), C.c_void_p]
     lib.splatt_b200_multi_env_devices.restype = C.c_int
     lib.splatt_b200_multi_env_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
     lib.splatt_b200_multi_create.restype = C.c_int

@@ -538,6 +538,14 @@ int splatt_b200_mttkrp_multicast(splatt_b200_tensor const * t, int mode, int nco
 int splatt_b200_mttkrp_multicast_sync(splatt_b200_tensor const * t, int mode, int ncolumns, int ldm,
                                       double const * const * d_mats, double * mc_out,
                                       splatt_b200_group_sync const * sync, void * stream) {
+  return splatt_b200_mttkrp_multicast_sync_columns(t, mode, ncolumns, ldm, d_mats, mc_out, 0, 0, sync,
+                                                   stream);
+}
+
+int splatt_b200_mttkrp_multicast_sync_columns(splatt_b200_tensor const * t, int mode, int ncolumns,
+                                              int ldm, double const * const * d_mats,
+                                              double * mc_out, int col_begin, int col_count,
+                                              splatt_b200_group_sync const * sync, void * stream) {
   if (!t || !d_mats || !mc_out || !sync || !sync->mc_flag || !sync->local_flag ||
       mode < 0 || mode >= t->nmodes) {
     fprintf(stderr, "SPLATT: splatt_b200_mttkrp_multicast_sync: bad arguments\n");
@@ -562,8 +570,8 @@ int splatt_b200_mttkrp_multicast_sync(splatt_b200_tensor const * t, int mode, in
     return SPLATT_ERROR_BADINPUT;
   }
   return spb200_launch_mttkrp(t->streams[p.stream], p.kind, p.outdepth, ncolumns, ldm, d_mats,
-                              mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true, 0, 0,
-                              &gs);
+                              mc_out, t->dims[mode], static_cast<cudaStream_t>(stream), true,
+                              col_begin, col_count, &gs);
 }
 
 int splatt_b200_csf_alloc(int nmodes, uint64_t const * dims, uint64_t nnz,

@@ -251,6 +251,8 @@ struct DevState {
   double * grams_local = nullptr;           // ... and of the k Gram slots
   cudaEvent_t ev_k = nullptr, ev_r = nullptr;
   cudaEvent_t ev_tail = nullptr;            // device 0: the mode's new factor is ready
+  cudaStream_t copy = nullptr;              // PCIe copies of the host-buffer call's column pipeline
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_kb[2] = {nullptr, nullptr};
   splatt_b200_als_tail * tail = nullptr;    // device 0 only (see splatt_b200_multi_cpd_als)
 };
 
@@ -332,6 +334,11 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
     MCK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_r, cudaEventDisableTiming));
     MCK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
+    MCK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      MCK(cudaEventCreateWithFlags(&s.ev_h2d[b], cudaEventDisableTiming));
+      MCK(cudaEventCreateWithFlags(&s.ev_kb[b], cudaEventDisableTiming));
+    }
     if (h->multicast) {
       char * base = reinterpret_cast<char *>(h->mc.uc[i]);
       MCK(cudaMemset(base, 0, h->mc.bytes));
@@ -548,6 +555,11 @@ void splatt_b200_multi_free(splatt_b200_multi * h) {
     if (s.ev_k) cudaEventDestroy(s.ev_k);
     if (s.ev_r) cudaEventDestroy(s.ev_r);
     if (s.ev_tail) cudaEventDestroy(s.ev_tail);
+    for (int b = 0; b < 2; ++b) {
+      if (s.ev_h2d[b]) cudaEventDestroy(s.ev_h2d[b]);
+      if (s.ev_kb[b]) cudaEventDestroy(s.ev_kb[b]);
+    }
+    if (s.copy) { cudaStreamSynchronize(s.copy); cudaStreamDestroy(s.copy); }
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.T) splatt_b200_tensor_free(s.T);
   }
@@ -655,6 +667,105 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
       MCK(cudaMallocHost(&h->stage_out, h->dims[mode] * J * 8));
       h->stage_out_cap = h->dims[mode] * J;
     }
+  }
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char * pe = getenv("SPLATT_B200_PIPELINE");
+    use_pipe = (pe && atoi(pe) == 0) ? 0 : 1;
+  }
+  if (h->multicast && use_pipe && J >= 16) {
+    // ---- column-block pipeline over all devices (same idea as dropin.cu:pipelined_call):
+    // MTTKRP is independent per column, so the factor columns of block 1 are packed and cross
+    // PCIe while the fused kernels run on block 0, and block 0's result slices return while the
+    // kernels run on block 1.  Per device: a copy stream for PCIe, the compute stream for the
+    // kernels (each with the group barrier in its tail), events between them.
+    const int rpad = (int)ld;
+    const int half = ((rpad / 2) + 1) & ~1;
+    const int cb[3] = {0, half, rpad};
+    const uint64_t I = h->dims[mode];
+    size_t in_off = 0, out_off[2] = {0, 0};
+    int rc = SPLATT_SUCCESS;
+    for (int b = 0; b < 2; ++b) {
+      const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+      const double * bsrc[SPB200_MAXN] = {nullptr};
+      size_t bpitch[SPB200_MAXN] = {0};
+      for (int m = 0; m < N; ++m) {
+        if (m == mode || !wcols) continue;
+        if (pinned) { bsrc[m] = mats[m] + c0; bpitch[m] = J * 8; continue; }
+        double * st = h->stage_in + in_off;              // dense rows x wcols
+        const double * from = mats[m] + c0;
+        const uint64_t rows = h->dims[m];
+#pragma omp parallel for schedule(static) num_threads(kHostTeam)
+        for (int64_t r = 0; r < (int64_t)rows; ++r)
+          memcpy(st + (size_t)r * wcols, from + (size_t)r * J, wcols * 8);
+        bsrc[m] = st; bpitch[m] = wcols * 8;
+        in_off += rows * wcols;
+      }
+      rc = for_each_device_parallel(k, [&](int i) -> int {
+        DevState & s = h->d[i];
+        MCK(cudaSetDevice(s.dev));
+        for (int m = 0; m < N; ++m)
+          if (m != mode && wcols)
+            MCK(cudaMemcpy2DAsync(s.mats[m] + c0, ld * 8, bsrc[m], bpitch[m], wcols * 8, h->dims[m],
+                                  cudaMemcpyHostToDevice, s.copy));
+        MCK(cudaEventRecord(s.ev_h2d[b], s.copy));
+        return SPLATT_SUCCESS;
+      });
+      if (rc != SPLATT_SUCCESS) return rc;
+    }
+    out_off[1] = I * std::min<size_t>(cb[1], J);
+    const uint32_t e0 = ++h->epoch, e1 = ++h->epoch;
+    rc = for_each_device_parallel(k, [&](int i) -> int {
+      DevState & s = h->d[i];
+      MCK(cudaSetDevice(s.dev));
+      const uint64_t r0 = I * i / k, r1 = I * (i + 1) / k;
+      for (int b = 0; b < 2; ++b) {
+        const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+        MCK(cudaStreamWaitEvent(s.stream, s.ev_h2d[b], 0));
+        splatt_b200_group_sync gs;
+        gs.mc_flag = h->mc_flag; gs.local_flag = s.flag_local; gs.target = b == 0 ? e0 : e1;
+        gs.rank = (uint32_t)i; gs.world = (uint32_t)k; gs.reserved = 0;
+        const int r = splatt_b200_mttkrp_multicast_sync_columns(s.T, mode, h->R, h->ldm, s.mats,
+                                                                h->mc_out[mode], cb[b],
+                                                                cb[b + 1] - cb[b], &gs, s.stream);
+        if (r != SPLATT_SUCCESS) return r;
+        MCK(cudaSetDevice(s.dev));
+        MCK(cudaEventRecord(s.ev_kb[b], s.stream));
+        MCK(cudaStreamWaitEvent(s.copy, s.ev_kb[b], 0));
+        if (r1 > r0 && wcols) {
+          if (pinned)
+            MCK(cudaMemcpy2DAsync(out_host + r0 * J + c0, J * 8, s.out[mode] + r0 * ld + c0, ld * 8,
+                                  wcols * 8, r1 - r0, cudaMemcpyDeviceToHost, s.copy));
+          else
+            MCK(cudaMemcpy2DAsync(h->stage_out + out_off[b] + r0 * wcols, wcols * 8,
+                                  s.out[mode] + r0 * ld + c0, ld * 8, wcols * 8, r1 - r0,
+                                  cudaMemcpyDeviceToHost, s.copy));
+        }
+      }
+      // buffer ready for its next use (after the slices have left it)
+      MCK(cudaMemsetAsync(s.out[mode], 0, I * ld * 8, s.copy));
+      return SPLATT_SUCCESS;
+    });
+    if (rc != SPLATT_SUCCESS) return rc;
+    for (int i = 0; i < k; ++i) {
+      MCK(cudaSetDevice(h->d[i].dev));
+      MCK(cudaStreamSynchronize(h->d[i].copy));
+      MCK(cudaStreamSynchronize(h->d[i].stream));
+    }
+    if (!pinned) {
+      for (int b = 0; b < 2; ++b) {
+        const size_t c0 = cb[b], wcols = std::min<size_t>(cb[b + 1], J) - std::min<size_t>(c0, J);
+        if (!wcols) continue;
+        const double * st = h->stage_out + out_off[b];
+        double * to = out_host + c0;
+#pragma omp parallel for schedule(static) num_threads(kHostTeam)
+        for (int64_t r = 0; r < (int64_t)I; ++r)
+          memcpy(to + (size_t)r * J, st + (size_t)r * wcols, wcols * 8);
+      }
+    }
+    cudaSetDevice(h->prev_dev);
+    h->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return SPLATT_SUCCESS;
   }
   size_t off = 0;
   for (int m = 0; m < N; ++m) {

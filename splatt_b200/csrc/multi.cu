@@ -392,8 +392,6 @@ int multi_alloc_buffers(splatt_b200_multi * h, int verbosity) {
   return SPLATT_SUCCESS;
 }
 
-// One MTTKRP over all devices; on return (in stream order of every device) out[d][mode]
-// holds the full sum on every device.
 // The fused kernel of device i for barrier sequence number `epoch`.
 int enqueue_mc_device(splatt_b200_multi * h, int i, int mode, uint32_t epoch) {
   DevState & s = h->d[i];
@@ -427,6 +425,8 @@ int for_each_device_parallel(int k, F f) {
   return rc_all;
 }
 
+// One MTTKRP over all devices; on return (in stream order of every device) out[d][mode]
+// holds the full sum on every device.
 int multi_mttkrp_enqueue(splatt_b200_multi * h, int mode) {
   const int k = h->k;
   if (h->multicast) {

@@ -606,7 +606,7 @@ def run_named(ctx, key, args, flush):
     step_ms, mode_ms, _ = wl.timed(flush, steps, max(args.warmup, 3))
     ms_per_step = ctx.max_over_ranks(float(np.sum(step_ms))) / steps
     per_mode = [ctx.max_over_ranks(float(np.mean(mode_ms[m]))) for m in range(wl.N)]
-    wl.keep_busy(flush, 0.5)
+    wl.keep_busy(flush, 0.3)
     clocks = sampler.stop() if sampler else None
     par = parity_vs_reference(ctx, f"named{key}", dims, ind_h, vals_h, wl.mats_h, ours)
     rec = None
@@ -704,10 +704,10 @@ def run_ours(args):
     worst_step = ctx.max_over_ranks(float(np.max(step_ms)))
     best_step = ctx.max_over_ranks(float(np.min(step_ms)))
     value = nnz_total * RANK * NMODES / (ms_per_step * 1e-3)
-    wl.keep_busy(flush, 1.0)               # clock samples under this very workload
+    wl.keep_busy(flush, 0.6)               # clock samples under this very workload
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["window"] = ("build + warm-up + timed region + 1 s of the same sweep loop right "
+        clocks["window"] = ("build + warm-up + timed region + 0.6 s of the same sweep loop right "
                             "after it (the timed region alone is shorter than the 100 ms "
                             "sampling period)")
     ind_h = vals_h = None

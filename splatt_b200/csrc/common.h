@@ -112,6 +112,7 @@ struct MttkrpArgs {
   int              ktiled;    // stream is leaf-tile ordered: keep non-leaf gathers out of L1
   int              multicast; // `out` is an NVLink multicast address: reduce with multimem.red
   int              rpad, apad; // shared-memory stagger: pad records / pad ids per group region (0 = none)
+  int              mc_store;   // multicast launches: rows owned by one lane group are stored, not reduced
   // Group barrier folded into the kernel's tail (multicast launches only; null = off):
   // after its last row reduction every CTA fences at system scope; the last CTA to finish
   // stores sync_target (the barrier's sequence number) into THIS GPU's slot of the group's

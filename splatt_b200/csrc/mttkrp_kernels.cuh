@@ -139,6 +139,15 @@ __device__ __forceinline__ void group_signal_and_wait(uint32_t * mc_flags, uint3
     } while (static_cast<int>(v - epoch) < 0);
   }
 }
+// A finished output row that no other lane group and no other GPU contributes to (a slice
+// lying wholly inside this group's record range) needs no reduction: one 128-bit store to the
+// multicast address writes it into every GPU's (zeroed) buffer -- half the NVLink packets of
+// two 64-bit multimem.red's and no work for the switch's reduction units.
+__device__ __forceinline__ void st_row_mc(char * __restrict__ base, uint32_t idx, uint32_t pitch,
+                                          double2 x) {
+  double * p = reinterpret_cast<double *>(base + static_cast<uint64_t>(idx) * pitch);
+  asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x.x), "d"(x.y) : "memory");
+}
 __device__ __forceinline__ double2 fma2(double s, double2 a, double2 c) {
   return make_double2(fma(s, a.x, c.x), fma(s, a.y, c.y));
 }
@@ -157,7 +166,7 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
                                             const double2 r, const double2 r2,
                                             double2 (&acc)[N - 1], uint32_t (&pos)[(N > 2) ? N - 2 : 1],
                                             const char * const (&mbase)[N], char * obase,
-                                            uint32_t pitch) {
+                                            uint32_t pitch, bool & seen_root, const bool last) {
   const double2  zero2 = make_double2(0.0, 0.0);
   const double   v     = __hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x));
   const uint32_t c     = q.w >> SPB200_IDX_BITS;
@@ -183,8 +192,16 @@ __device__ __forceinline__ void root_record(const MttkrpArgs & a, const uint4 q,
       if (c >= uint32_t(N - 1)) {
         const uint32_t row = __ldg(&a.up[0][pos[0]]);
         ++pos[0];
-        if constexpr (MC) red_row_mc(obase, row, pitch, acc[0]);
-        else red_row(obase, row, pitch, acc[0]);
+        if constexpr (MC) {
+          // the first slice a group closes may have begun before its range and the slice cut by
+          // the range's end continues after it: those are partial rows (reduce); every slice in
+          // between lies wholly inside the range (store)
+          if (a.mc_store && seen_root && !last) st_row_mc(obase, row, pitch, acc[0]);
+          else red_row_mc(obase, row, pitch, acc[0]);
+        } else {
+          red_row(obase, row, pitch, acc[0]);
+        }
+        seen_root = true;
         acc[0] = zero2;
       }
     }
@@ -285,6 +302,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
 #pragma unroll
   for (int l = 0; l < N - 2; ++l) pos[l] = T ? a.desc[cb * (N - 2) + l] : 0u;
   uint32_t  pc = N - 1;        // close count of the previous record
+  bool      seen_root = false; // this group has closed a root slice already (multicast store rule)
   const int d  = a.outdepth;
 
 #pragma unroll
@@ -380,7 +398,8 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
           } else {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
-              root_record<N, MC>(a, q[u], b[u], r[u], r2[u], acc, pos, mbase, obase, pitch);
+              root_record<N, MC>(a, q[u], b[u], r[u], r2[u], acc, pos, mbase, obase, pitch, seen_root,
+                                 off + n0 + u + 1 == T);
           }
         }
         for (; n0 < cnt; ++n0) {   // tail of the range's last stage
@@ -391,7 +410,7 @@ mttkrp_stream_kernel(const MttkrpArgs a) {
           if constexpr (N >= 4) {
             if ((q.w >> SPB200_IDX_BITS) >= 2u) r2 = ld_row(mbase[N - 3], abuf[n0], pitch);
           }
-          root_record<N, MC>(a, q, b, r, r2, acc, pos, mbase, obase, pitch);
+          root_record<N, MC>(a, q, b, r, r2, acc, pos, mbase, obase, pitch, seen_root, off + n0 + 1 == T);
         }
       } else if constexpr (KIND == SPB200_KIND_INTL) {
 #pragma unroll 2

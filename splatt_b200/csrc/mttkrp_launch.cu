@@ -145,6 +145,14 @@ int spb200_launch_mttkrp(const FiberStream & s, int kind, int outdepth, int ncol
     }
     a.rpad = stagger >= 1 ? 1 : 0;
     a.apad = stagger >= 2 ? 4 : 0;
+    // SPLATT_B200_MC_STORE=0: reduce every row of a multicast launch (the round-1 behaviour)
+    static int mc_store = -1;
+    if (mc_store < 0) {
+      const char * e = getenv("SPLATT_B200_MC_STORE");
+      mc_store = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    // (a leaf-tiled stream closes the same root row once per tile: never stored)
+    a.mc_store = (mc_store && !s.ktile_rows) ? 1 : 0;
   }
 
   const int num_sms = num_sms_of_current_device();

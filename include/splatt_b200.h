@@ -355,10 +355,13 @@ int splatt_b200_mttkrp_columns(
 /* Fused MTTKRP + exchange for sharded tensors on one NVSwitch domain.  `mc_out` is
  * an NVLink MULTICAST address (CUDA multicast object / torch symmetric memory
  * `multicast_ptr`) bound to one dims[mode] x ldm buffer on every GPU of the
- * group.  The kernel adds every finished output row into ALL the buffers with
- * `multimem.red.add.f64` as it goes, so the per-mode all-reduce of the north star
- * happens inside the MTTKRP kernel instead of after it.  Contract: every rank
- * zeroes its own buffer and the group synchronises BEFORE the call; after the
+ * group.  The kernel puts every finished output row into ALL the buffers as it
+ * goes -- `multimem.red.add.f64` for rows that several lane groups or GPUs
+ * contribute to, a plain 128-bit store to the multicast address for rows one lane
+ * group finishes alone (SPLATT_B200_MC_STORE=0: reductions only) -- so the per-mode
+ * all-reduce of the north star happens inside the MTTKRP kernel instead of after
+ * it.  Contract: every rank zeroes its own buffer and the group synchronises BEFORE
+ * the call (the call does NOT accumulate into what the buffers held); after the
  * call the group synchronises once more and every buffer holds the full sum.
  * Requires the ALLROOT layout (root kernels).  Not zeroed, not synchronised here. */
 int splatt_b200_mttkrp_multicast(

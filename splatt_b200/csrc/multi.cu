@@ -3,14 +3,16 @@
 // This is the C-ABI counterpart of the reference's distributed driver
 // (mpi_cpd_als_iterate, src/mpi/mpi_cpd.c:627-804; per-mode reduction :250-308) for one
 // node: the tensor is partitioned, every device computes the MTTKRP of its share, the
-// output factor is summed over devices once per mode, the dense tail runs replicated.
+// output factor is summed over devices once per mode, the dense tail is row-partitioned
+// over the devices (single-valued factors; see splatt_b200_multi_cpd_als).
 // Differences that make it B200-native:
 //   * partition = equal-nnz contiguous chunk ranges of every fiber stream (built once on
 //     the first device, the shares are cut out and moved device-to-device);
-//   * exchange  = inside the MTTKRP kernel: every finished output row is added into ALL
-//     devices' buffers with multimem.red.add.f64 on an NVLink multicast mapping created
-//     here with the CUDA driver's multicast objects (no NCCL, no torch), and the group
-//     barrier is the kernel's own tail (mttkrp_kernels.cuh);
+//   * exchange  = inside the MTTKRP kernel: every finished output row goes into ALL devices'
+//     buffers through an NVLink multicast mapping created here with the CUDA driver's
+//     multicast objects (no NCCL, no torch) -- multimem.red.add.f64 for rows shared between
+//     lane groups or devices, a plain 128-bit store for rows one lane group finishes alone --
+//     and the group barrier is the kernel's own tail (mttkrp_kernels.cuh);
 //   * fallback  = when the box has no multicast support: local kernels, then a peer-memory
 //     reduce kernel (each device sums one row slice over all peers' partials and writes
 //     the sum into every peer's result buffer), ordered with CUDA events.
@@ -833,9 +835,12 @@ int splatt_b200_multi_mttkrp_host(splatt_b200_multi * h, int mode, double const 
 }
 
 // CPD-ALS over all devices: per mode the fused MTTKRP + exchange on every device, then the
-// dense tail ONCE, on device 0 (the same kernels splatt_cpd_als uses on one GPU), whose new
-// factor every other device pulls over NVLink before its next MTTKRP.  The factor matrices
-// are therefore single-valued: replicated tails would agree only to rounding (their
+// dense tail ONCE -- row-partitioned over the devices when the multicast mapping exists (each
+// device solves, normalises and Grams its own row slice and multicasts it; partial norms and
+// Grams are summed in device order on every device), otherwise on device 0 (the same kernels
+// splatt_cpd_als uses on one GPU), whose new factor every other device pulls over NVLink
+// before its next MTTKRP.  Either way the factor matrices
+// are single-valued: replicated tails would agree only to rounding (their
 // atomics and the multimem.red's arrive in a different order on every GPU) and on
 // ill-conditioned problems such replicas drift apart until the shards multiply with
 // inconsistent factors (measured: 300^3, 200 K nnz, rank 32 diverges after ~10 iterations).
@@ -1075,7 +1080,7 @@ int splatt_b200_multi_cpd_als(splatt_b200_multi * h, splatt_csf const * tensors,
     printf("SPLATT-B200: multi CPD phases (ms, all iterations): mttkrp %.2f | solve+norm %.2f | "
            "scale+gram %.2f | gram sum+release %.2f | fit/other %.2f\n",
            tphase[0], tphase[1], tphase[2], tphase[3], tphase[4]);
-  // factors back from device 0 (replicas agree to rounding)
+  // factors back from device 0 (every device holds the same bits)
   {
     DevState & s = h->d[0];
     if (cudaSetDevice(s.dev) != cudaSuccess) return fail(SPLATT_ERROR_BADINPUT);

@@ -114,3 +114,20 @@ def test_multi_gpu_engine_rejects_bad_arguments(lib):
     lib.splatt_b200_multi_free(None)
     lib.splatt_b200_cache_clear()                       # empty cache: a no-op
     assert lib.splatt_b200_build_count() == 0
+
+
+def test_every_environment_switch_is_documented():
+    """Every SPLATT_B200_* variable the sources read appears in DESIGN.md (section 9)."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    names = set()
+    for f in list((root / "splatt_b200" / "csrc").glob("*.cu*")) + list((root / "splatt_b200").glob("*.py")) \
+            + [root / "bench.py"]:
+        text = f.read_text()
+        names |= set(re.findall(r'getenv\("(SPLATT_B200_[A-Z0-9_]+)"\)', text))
+        names |= set(re.findall(r'environ(?:\.get)?[\[(]"(SPLATT_B200_[A-Z0-9_]+)"', text))
+    assert len(names) > 10
+    design = (root / "DESIGN.md").read_text()
+    missing = sorted(n for n in names if n not in design)
+    assert not missing, missing
